@@ -1,0 +1,188 @@
+/*
+ * sonics_b200.h -- C-ABI of the B200-native SONiCS Monte-Carlo engine.
+ *
+ * This is the drop-in boundary for the reference's hot path.  In the reference
+ * the CLI script imports the compiled extension module `sonics` and calls
+ *     sonics.get_alleles(genotype_str)                         (sonics:350)
+ *     sonics.monte_carlo(reps, constants, ranges, options)     (sonics:427-432)
+ * which in turn run one_repeat()/simulate() (sonics.pyx:293-480) and the f2py
+ * routine pymc_extracted.mvhyperg (pymc_extracted.f:63-109).  A maintainer
+ * binds the functions below with ctypes; the Python shim
+ * sonics_b200/sonics.py re-exposes get_alleles()/monte_carlo()/one_repeat()
+ * with the reference's signatures on top of them.
+ *
+ * Conventions: extern "C", plain pointers and sizes, int status (0 = ok,
+ * negative = error; sonics_last_error() gives the message of the calling
+ * thread's last failure), no exceptions cross the boundary.  The library never
+ * allocates device memory: every device buffer (tables, lnL arrays, workspace)
+ * is owned by the caller (PyTorch tensors in the Python host) and passed as a
+ * raw device pointer.  All work is enqueued on the CUDA stream handle passed in
+ * (`stream`, a cudaStream_t cast to void*; NULL = legacy default stream) and is
+ * asynchronous unless stated otherwise.  One ctx per GPU; a ctx is not
+ * thread-safe (one host thread per GPU).
+ *
+ * There is no CPU fallback: every entry point that computes fails with
+ * SONICS_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef SONICS_B200_H
+#define SONICS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SONICS_ABI_VERSION 1
+#define SONICS_MAX_ALLELE 500      /* get_alleles(): max_allele, sonics.pyx:21 */
+#define SONICS_SENTINEL (-999999.0) /* lnL when reads > pool, sonics.pyx:360-361 */
+
+enum {
+    SONICS_OK = 0,
+    SONICS_ERR_ARG = -1,     /* bad argument (null pointer, size, range) */
+    SONICS_ERR_CUDA = -2,    /* CUDA runtime / no usable device */
+    SONICS_ERR_ALLELES = -3, /* "Less then two alleles as starting conditions!" sonics.pyx:316-318 */
+    SONICS_ERR_RANGE = -4,   /* allele index or molecule count outside the supported range */
+    SONICS_ERR_SPACE = -5    /* caller-provided buffer too small */
+};
+
+/* FILTER bits of a verdict (sonics.pyx:244-252; label strings in the same order) */
+enum {
+    SONICS_FILTER_PASS = 1,
+    SONICS_FILTER_MWU_TEST = 2,
+    SONICS_FILTER_BEST_RATIO = 4,
+    SONICS_FILTER_PERCENTILE_RATIO = 8,
+    SONICS_FILTER_NO_SUCCESS = 16
+};
+
+typedef struct sonics_ctx sonics_ctx;
+
+/* The `constants` / `ranges` / `options` dicts frozen into a POD
+ * (sonics:714-751; keys consumed at sonics.pyx:67-82,302-337,405-410). */
+typedef struct SonicsParams {
+    int32_t n_cycles;      /* constants['n_cycles'] = pcr_cycles + after_capture        */
+    int32_t capture_cycle; /* constants['capture_cycle'] = pcr_cycles + 1                */
+    int32_t floor_opt;     /* constants['floor']; -1 => minimum repeat count 1           */
+    int32_t random_start;  /* constants['random']                                        */
+    int32_t up_preference; /* constants['up_preference']                                 */
+    int32_t start_copies;  /* constants['start_copies']                                  */
+    int32_t min_sim;       /* options['min_sim']                                         */
+    int32_t monte_carlo;   /* options['monte_carlo']                                     */
+    double down[2];        /* ranges[0] = (min, max)                                     */
+    double up[2];          /* ranges[1]                                                  */
+    double capture[2];     /* ranges[2]                                                  */
+    double efficiency[2];  /* ranges[3]                                                  */
+    double padjust;        /* constants['padjust']                                       */
+    double lnL_threshold;  /* constants['lnL_threshold']                                 */
+} SonicsParams;
+
+/* One verdict per genotype: everything monte_carlo() prints (sonics.pyx:254-265). */
+typedef struct SonicsVerdict {
+    int32_t allele_lo, allele_hi; /* called genotype "lo/hi"; -1/-1 = "./."             */
+    int32_t filter;               /* SONICS_FILTER_* bits                               */
+    int32_t run_reps;             /* simulations run                                    */
+    int32_t min_sim;              /* min over groups of #(lnL > sentinel)               */
+    int32_t best_sim;             /* simulation index of the reported (best) row        */
+    int32_t n_groups;
+    int32_t p_clamped;            /* 1 when high_pval was clamped to the int 1 (:225)   */
+    double lnL;                   /* best row                                           */
+    double identity;              /* best row (replayed)                                */
+    double r_squared;             /* best row (replayed), float32 widened               */
+    double high_pval;             /* Bonferroni-scaled max MWU p                        */
+    double best_lnL_ratio;
+    double percentile_lnL_ratio;
+    /* --monte_carlo extras (sonics.pyx:119-131): 75th percentiles within the best group */
+    double identity_q75, r_squared_q75, lnL_q75;
+} SonicsVerdict;
+
+int sonics_abi_version(void);
+const char *sonics_last_error(void);
+
+/* Context bound to one CUDA device (must be sm_100). */
+int sonics_create(int device, sonics_ctx **out);
+void sonics_destroy(sonics_ctx *ctx);
+/* Block until everything enqueued on `stream` has finished. */
+int sonics_sync(sonics_ctx *ctx, void *stream);
+
+/* pymc_extracted.mvhyperg (pymc_extracted.f:63-109; f2py signature :76-79),
+ * evaluated on the device in fp64 with the reference's NR-Lanczos gammln in the
+ * reference's operation order.  x, color: HOST arrays of n_pools rows of k
+ * int64; like_out: HOST array of n_pools doubles.  Synchronous.
+ * dev_scratch: caller-owned device buffer of >= n_pools*(2*k*8 + 8) bytes. */
+int sonics_mvhyperg(sonics_ctx *ctx, const int64_t *x, const int64_t *color, int k, int n_pools, double *like_out,
+                    void *dev_scratch, size_t dev_scratch_bytes);
+
+/* ---- genotype table -------------------------------------------------- */
+/* A genotype (one locus x sample read-support string, get_alleles() output,
+ * sonics.pyx:17-31) is given in CSR form: its non-zero alleles
+ * allele[allele_off[g] .. allele_off[g+1]) ascending, with reads[] > 0.
+ * noise_coef[g] is constants['noise_coef'] (sonics:407-419), applied as the
+ * reference does through a C float.  uid[g] (nullable => g) keys the RNG stream
+ * so results do not depend on how genotypes are sharded across GPUs. */
+size_t sonics_table_bytes(int n_gt, int n_alleles_total);
+int sonics_table_build(sonics_ctx *ctx, const SonicsParams *params, int n_gt, const int32_t *allele_off,
+                       const int32_t *allele, const int32_t *reads, const float *noise_coef, const uint32_t *uid,
+                       void *dev_table, size_t dev_table_bytes, void *stream);
+/* Largest live window (histogram bins) over the table: sizes shared memory. */
+int sonics_table_max_window(sonics_ctx *ctx);
+
+/* ---- K1: fixed-count simulations (one_repeat() x sim_count per genotype) --
+ * For every genotype g listed in dev_active (all n_gt when dev_active is NULL)
+ * run simulations j = sim_begin .. sim_begin+sim_count-1 (sonics.pyx:293-394
+ * incl. simulate() :397-480 and the lnL :360-363) and store
+ *   dev_lnL  [g*out_stride + j]   fp64 lnL or SONICS_SENTINEL
+ *   dev_group[g*out_stride + j]   u16 group id = lo_idx*n_alleles + hi_idx, the indices (into the
+ *                                 genotype's allele list) of the two start alleles, lo_idx <= hi_idx
+ * and, when the pointers are non-NULL,
+ *   dev_identity (fp64), dev_rsq (fp32; a C float in the reference, sonics.pyx:300): descriptors of
+ *                                 the simulated sequencing readout, sonics.pyx:341-357,365-384
+ *   dev_simpar [4*(g*out_stride + j)]   fp64 down, up, capture, efficiency (the report columns :387-393).
+ * The RNG is Philox4x32-10 keyed by (seed; uid, j): results do not depend on
+ * launch geometry, on sim_begin/sim_count splits, or on the GPU that runs them. */
+int sonics_simulate(sonics_ctx *ctx, const SonicsParams *params, const void *dev_table, int n_gt,
+                    const int32_t *dev_active, int n_active, int64_t sim_begin, int64_t sim_count, uint64_t seed,
+                    int64_t out_stride, double *dev_lnL, uint16_t *dev_group, double *dev_identity, float *dev_rsq,
+                    double *dev_simpar, void *stream);
+
+/* ---- K2/K3: per-genotype statistics on the cumulative lnL arrays ---------
+ * Restates sonics.pyx:136-191 (+ :208-252 for the final verdict): grouping,
+ * min_sim, top-2 groups by max lnL, 75th-percentile difference, one-sided
+ * Mann-Whitney U of the best group against every other group with Bonferroni,
+ * PASS predicate.  n_run = cumulative simulations per genotype.  final != 0
+ * also fills the FILTER bits of a non-passing genotype.  Verdicts are written to
+ * dev_verdict[slot]. */
+int sonics_evaluate(sonics_ctx *ctx, const SonicsParams *params, const void *dev_table, int n_gt,
+                    const int32_t *dev_active, int n_active, int64_t n_run, int64_t out_stride, const double *dev_lnL,
+                    const uint16_t *dev_group, int final_round, SonicsVerdict *dev_verdict, void *stream);
+
+/* ---- the whole repeat-until-pass loop for a batch of genotypes ------------
+ * Equivalent of mapping process_one_genotype() -> monte_carlo() over the list
+ * (sonics:216-228): rounds at 100/500/1000/5000... cumulative simulations
+ * (sonics.pyx:79-82,193-199), statistics on the device after each round,
+ * compaction of the genotypes that passed, replay of the best simulation for
+ * identity / r^2.  Inputs and verdict_out are HOST buffers; dev_work is a
+ * caller-owned device buffer of >= sonics_genotype_work_bytes(...) bytes.
+ * Synchronous (returns when verdict_out is filled). */
+size_t sonics_genotype_work_bytes(int n_gt, int n_alleles_total, int max_reps);
+int sonics_genotype_batch(sonics_ctx *ctx, const SonicsParams *params, int n_gt, const int32_t *allele_off,
+                          const int32_t *allele, const int32_t *reads, const float *noise_coef, const uint32_t *uid,
+                          int max_reps, uint64_t seed, SonicsVerdict *verdict_out, void *dev_work,
+                          size_t dev_work_bytes, void *stream);
+
+/* ---- test hooks (unit tests of the device RNG and samplers) ---------------
+ * sonics_debug_philox:  n_blocks x 4 u32 of the Philox4x32-10 stream (seed; sim, uid, stream).
+ * sonics_debug_sample:  count draws, one per thread (thread t uses sim = t), of
+ *      kind 0: Binomial(n, p)    kind 1: Poisson(lam = p)
+ * into dev_out (int32).  Both synchronous; dev_out is caller-owned device memory. */
+int sonics_debug_philox(sonics_ctx *ctx, uint64_t seed, uint64_t sim, uint32_t uid, uint32_t stream_id, int n_blocks,
+                        uint32_t *dev_out);
+int sonics_debug_sample(sonics_ctx *ctx, int kind, int n, double p, int64_t count, uint64_t seed, int32_t *dev_out);
+
+/* Kernel launches issued by this ctx so far (bench.py's gpu_launches). */
+int64_t sonics_launch_count(sonics_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SONICS_B200_H */

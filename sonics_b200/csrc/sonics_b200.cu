@@ -1,0 +1,376 @@
+// C-ABI of the B200-native SONiCS engine (see include/sonics_b200.h).
+// Host side: argument checking, genotype-table packing, launch configuration.
+// No device memory is allocated here; all device buffers belong to the caller.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/sonics_b200.h"
+#include "sim_kernel.cuh"
+#include "stats_kernel.cuh"
+
+using namespace sonics;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_OK(expr)                                                                                        \
+    do {                                                                                                     \
+        cudaError_t e__ = (expr);                                                                            \
+        if (e__ != cudaSuccess)                                                                              \
+            return fail(SONICS_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__));                   \
+    } while (0)
+
+struct TableInfo {
+    int n_gt, n_alleles, max_W;
+    size_t off_allele, off_reads, off_fl;
+};
+
+struct sonics_ctx {
+    int device;
+    int sm_count;
+    int64_t launches;
+    int max_W_last;
+    std::map<const void *, TableInfo> tables;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static void table_layout(int n_gt, int n_alleles, TableInfo &ti)
+{
+    ti.n_gt = n_gt;
+    ti.n_alleles = n_alleles;
+    ti.off_allele = align_up((size_t)n_gt * sizeof(GtHeader), 16);
+    ti.off_reads = ti.off_allele + align_up((size_t)n_alleles * 4, 16);
+    ti.off_fl = ti.off_reads + align_up((size_t)n_alleles * 4, 16);
+}
+
+extern "C" {
+
+int sonics_abi_version(void) { return SONICS_ABI_VERSION; }
+const char *sonics_last_error(void) { return g_err.c_str(); }
+
+int sonics_create(int device, sonics_ctx **out)
+{
+    if (!out)
+        return fail(SONICS_ERR_ARG, "sonics_create: out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(SONICS_ERR_CUDA, "sonics_create: no CUDA device (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n)
+        return fail(SONICS_ERR_ARG, "sonics_create: device %d out of range (%d devices)", device, n);
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(SONICS_ERR_CUDA, "sonics_create: device %d is sm_%d%d; this build carries sm_100a code only", device,
+                    prop.major, prop.minor);
+    CUDA_OK(cudaSetDevice(device));
+    sonics_ctx *c = new sonics_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->launches = 0;
+    c->max_W_last = 0;
+    *out = c;
+    return SONICS_OK;
+}
+
+void sonics_destroy(sonics_ctx *ctx) { delete ctx; }
+
+int sonics_sync(sonics_ctx *ctx, void *stream)
+{
+    if (!ctx)
+        return fail(SONICS_ERR_ARG, "sonics_sync: ctx is NULL");
+    CUDA_OK(cudaSetDevice(ctx->device));
+    CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    return SONICS_OK;
+}
+
+int64_t sonics_launch_count(sonics_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int sonics_mvhyperg(sonics_ctx *ctx, const int64_t *x, const int64_t *color, int k, int n_pools, double *like_out,
+                    void *dev_scratch, size_t dev_scratch_bytes)
+{
+    if (!ctx || !x || !color || !like_out || !dev_scratch)
+        return fail(SONICS_ERR_ARG, "sonics_mvhyperg: NULL argument");
+    if (k <= 0 || n_pools <= 0)
+        return fail(SONICS_ERR_ARG, "sonics_mvhyperg: k and n_pools must be positive");
+    const size_t row = (size_t)k * 8, need = (size_t)n_pools * (2 * row + 8);
+    if (dev_scratch_bytes < need)
+        return fail(SONICS_ERR_SPACE, "sonics_mvhyperg: scratch %zu < %zu bytes", dev_scratch_bytes, need);
+    CUDA_OK(cudaSetDevice(ctx->device));
+    int64_t *dx = (int64_t *)dev_scratch;
+    int64_t *dc = dx + (size_t)n_pools * k;
+    double *dout = (double *)(dc + (size_t)n_pools * k);
+    CUDA_OK(cudaMemcpy(dx, x, (size_t)n_pools * row, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(dc, color, (size_t)n_pools * row, cudaMemcpyHostToDevice));
+    k_mvhyperg<<<(n_pools + 127) / 128, 128>>>(dx, dc, k, n_pools, dout);
+    ctx->launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpy(like_out, dout, (size_t)n_pools * 8, cudaMemcpyDeviceToHost));
+    return SONICS_OK;
+}
+
+size_t sonics_table_bytes(int n_gt, int n_alleles_total)
+{
+    if (n_gt < 0 || n_alleles_total < 0)
+        return 0;
+    TableInfo ti;
+    table_layout(n_gt, n_alleles_total, ti);
+    return ti.off_fl + align_up((size_t)n_alleles_total * 8, 16);
+}
+
+static int check_params(const SonicsParams *p)
+{
+    if (!p)
+        return fail(SONICS_ERR_ARG, "params is NULL");
+    if (p->n_cycles < 0 || p->n_cycles > 400)
+        return fail(SONICS_ERR_ARG, "n_cycles %d outside [0, 400]", p->n_cycles);
+    if (p->start_copies < 0)
+        return fail(SONICS_ERR_ARG, "start_copies must be >= 0");
+    // counts are held in int32 on the device
+    const double growth = (double)p->start_copies * std::pow(1.0 + std::max(0.0, p->efficiency[1]), p->n_cycles);
+    if (growth * 1.25 >= 2147483647.0)
+        return fail(SONICS_ERR_RANGE, "start_copies * (1 + efficiency_max)^n_cycles = %.3g overflows int32 counts",
+                    growth);
+    return SONICS_OK;
+}
+
+static SimParamsDev dev_params(const SonicsParams *p)
+{
+    const double small_number = 1e-16; // sonics.pyx:36
+    SimParamsDev d;
+    d.n_cycles = p->n_cycles;
+    d.capture_cycle = p->capture_cycle;
+    d.random_start = p->random_start;
+    d.up_preference = p->up_preference;
+    d.half_copies = (int32_t)((double)p->start_copies / 2.0); // :326-327, truncation into the int array
+    d.down_lo = p->down[0] + small_number;
+    d.down_rng = p->down[1] - d.down_lo;
+    d.up_lo = p->up[0] + small_number;
+    d.up_hi = p->up[1];
+    d.cap_lo = p->capture[0] + small_number;
+    d.cap_rng = p->capture[1] - d.cap_lo;
+    d.eff_lo = p->efficiency[0] + small_number;
+    d.eff_rng = p->efficiency[1] - d.eff_lo;
+    return d;
+}
+
+int sonics_table_build(sonics_ctx *ctx, const SonicsParams *params, int n_gt, const int32_t *allele_off,
+                       const int32_t *allele, const int32_t *reads, const float *noise_coef, const uint32_t *uid,
+                       void *dev_table, size_t dev_table_bytes, void *stream)
+{
+    if (!ctx || !allele_off || !allele || !reads || !dev_table)
+        return fail(SONICS_ERR_ARG, "sonics_table_build: NULL argument");
+    if (int rc = check_params(params))
+        return rc;
+    if (n_gt <= 0)
+        return fail(SONICS_ERR_ARG, "sonics_table_build: n_gt must be positive");
+    const int nA = allele_off[n_gt];
+    if (allele_off[0] != 0 || nA <= 0)
+        return fail(SONICS_ERR_ARG, "sonics_table_build: malformed allele_off");
+    const size_t need = sonics_table_bytes(n_gt, nA);
+    if (dev_table_bytes < need)
+        return fail(SONICS_ERR_SPACE, "sonics_table_build: table buffer %zu < %zu bytes", dev_table_bytes, need);
+    TableInfo ti;
+    table_layout(n_gt, nA, ti);
+    std::vector<unsigned char> host(ti.off_fl, 0);
+    GtHeader *hdr = (GtHeader *)host.data();
+    int32_t *h_allele = (int32_t *)(host.data() + ti.off_allele);
+    int32_t *h_reads = (int32_t *)(host.data() + ti.off_reads);
+    int max_W = 0;
+    const int64_t sum0 = 2 * (int64_t)((double)params->start_copies / 2.0);
+    for (int g = 0; g < n_gt; ++g) {
+        const int a0 = allele_off[g], a1 = allele_off[g + 1], A = a1 - a0;
+        if (A < 2)
+            return fail(SONICS_ERR_ALLELES, "genotype %d: Less then two alleles as starting conditions! Aborting.", g);
+        if (A > 255)
+            return fail(SONICS_ERR_RANGE, "genotype %d: %d alleles (max 255)", g, A);
+        int64_t D = 0;
+        int first = 0;
+        for (int i = a0; i < a1; ++i) {
+            if (allele[i] <= 0 || allele[i] >= SONICS_MAX_ALLELE)
+                return fail(SONICS_ERR_RANGE, "genotype %d: allele %d outside (0, %d)", g, allele[i], SONICS_MAX_ALLELE);
+            if (i > a0 && allele[i] <= allele[i - 1])
+                return fail(SONICS_ERR_ARG, "genotype %d: alleles must be strictly ascending", g);
+            if (reads[i] <= 0)
+                return fail(SONICS_ERR_ARG, "genotype %d: reads must be positive", g);
+            D += reads[i];
+            if (reads[i] > reads[a0 + first])
+                first = i - a0; // np.argmax: first occurrence of the maximum (:323)
+            h_allele[i] = allele[i];
+            h_reads[i] = reads[i];
+        }
+        if (D >= 2147483647)
+            return fail(SONICS_ERR_RANGE, "genotype %d: read total overflows int32", g);
+        const int min_in = allele[a0], max_in = allele[a1 - 1];
+        int floor_al;
+        if (params->floor_opt == -1)
+            floor_al = 1;
+        else
+            floor_al = std::max(1, min_in - params->floor_opt);
+        // bins that can ever hold molecules: down-stutter walks one bin per cycle and stops at
+        // floor-1 (:427,472); up-stutter walks one bin per cycle (:476)
+        int lo = std::max(floor_al - 1, min_in - params->n_cycles);
+        lo = std::max(0, std::min(lo, min_in));
+        const int hi = max_in + params->n_cycles;
+        if (hi >= SONICS_MAX_ALLELE)
+            return fail(SONICS_ERR_RANGE, "genotype %d: allele %d + %d cycles leaves the %d-bin histogram", g, max_in,
+                        params->n_cycles, SONICS_MAX_ALLELE);
+        GtHeader &h = hdr[g];
+        h.a_off = a0;
+        h.n_alleles = A;
+        h.lo = lo;
+        h.W = hi - lo + 1;
+        h.floor_al = floor_al;
+        h.first_idx = first;
+        h.D = (int32_t)D;
+        const float nc = noise_coef ? noise_coef[g] : 0.0f;
+        h.noise_add = nc > 0.0f ? (int32_t)((double)nc * (double)sum0) : 0; // :334-337
+        h.uid = uid ? uid[g] : (uint32_t)g;
+        h.in_lo_bin = min_in - lo;
+        h.fl_D = 0.0;
+        max_W = std::max(max_W, h.W);
+    }
+    ti.max_W = max_W;
+    CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_OK(cudaMemcpyAsync(dev_table, host.data(), host.size(), cudaMemcpyHostToDevice, s));
+    // pageable source: the copy is staged before the call returns, `host` may go out of scope
+    unsigned char *base = (unsigned char *)dev_table;
+    const int n_thr = std::max(n_gt, nA);
+    k_table_prep<<<(n_thr + 255) / 256, 256, 0, s>>>((GtHeader *)base, (const int32_t *)(base + ti.off_reads),
+                                                      (double *)(base + ti.off_fl), n_gt, nA);
+    ctx->launches++;
+    CUDA_OK(cudaGetLastError());
+    ctx->tables[dev_table] = ti;
+    ctx->max_W_last = max_W;
+    return SONICS_OK;
+}
+
+int sonics_table_max_window(sonics_ctx *ctx) { return ctx ? ctx->max_W_last : 0; }
+
+static int find_table(sonics_ctx *ctx, const void *dev_table, int n_gt, TableInfo &ti, TableView &tv)
+{
+    auto it = ctx->tables.find(dev_table);
+    if (it == ctx->tables.end())
+        return fail(SONICS_ERR_ARG, "unknown genotype table %p (call sonics_table_build first)", dev_table);
+    ti = it->second;
+    if (ti.n_gt != n_gt)
+        return fail(SONICS_ERR_ARG, "table holds %d genotypes, call says %d", ti.n_gt, n_gt);
+    const unsigned char *base = (const unsigned char *)dev_table;
+    tv.hdr = (const GtHeader *)base;
+    tv.allele = (const int32_t *)(base + ti.off_allele);
+    tv.reads = (const int32_t *)(base + ti.off_reads);
+    tv.fl_reads = (const double *)(base + ti.off_fl);
+    return SONICS_OK;
+}
+
+int sonics_simulate(sonics_ctx *ctx, const SonicsParams *params, const void *dev_table, int n_gt,
+                    const int32_t *dev_active, int n_active, int64_t sim_begin, int64_t sim_count, uint64_t seed,
+                    int64_t out_stride, double *dev_lnL, uint16_t *dev_group, double *dev_identity, float *dev_rsq,
+                    double *dev_simpar, void *stream)
+{
+    if (!ctx || !dev_table || !dev_lnL || !dev_group)
+        return fail(SONICS_ERR_ARG, "sonics_simulate: NULL argument");
+    if (int rc = check_params(params))
+        return rc;
+    if (sim_count <= 0 || sim_begin < 0)
+        return fail(SONICS_ERR_ARG, "sonics_simulate: bad simulation range");
+    if (out_stride < sim_begin + sim_count)
+        return fail(SONICS_ERR_SPACE, "sonics_simulate: out_stride %lld < sim_begin + sim_count", (long long)out_stride);
+    TableInfo ti;
+    TableView tv;
+    if (int rc = find_table(ctx, dev_table, n_gt, ti, tv))
+        return rc;
+    if (!dev_active)
+        n_active = n_gt;
+    if (n_active <= 0)
+        return SONICS_OK;
+    CUDA_OK(cudaSetDevice(ctx->device));
+    SimArgs a;
+    a.t = tv;
+    a.p = dev_params(params);
+    a.active = dev_active;
+    a.n_active = n_active;
+    const int64_t wpg = (sim_count + 31) / 32;
+    if (wpg > 2147483647LL)
+        return fail(SONICS_ERR_RANGE, "sonics_simulate: sim_count too large");
+    a.warps_per_gt = (int32_t)wpg;
+    a.sim_begin = sim_begin;
+    a.sim_count = sim_count;
+    a.seed = seed;
+    a.out_stride = out_stride;
+    a.lnL = dev_lnL;
+    a.group = dev_group;
+    a.identity = dev_identity;
+    a.rsq = dev_rsq;
+    a.simpar = dev_simpar;
+    a.Wcap = ti.max_W;
+    const bool readout = dev_identity != nullptr || dev_rsq != nullptr;
+    const size_t per_warp = warp_smem_bytes(a.Wcap);
+    int wpb = (int)std::min<size_t>(4, (200 * 1024) / per_warp);
+    if (wpb < 1)
+        return fail(SONICS_ERR_RANGE, "window of %d bins does not fit shared memory", a.Wcap);
+    const size_t smem = per_warp * wpb;
+    auto kern = readout ? k_simulate<true> : k_simulate<false>;
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
+    if (occ < 1)
+        occ = 1;
+    const int64_t n_items = (int64_t)n_active * wpg;
+    const int64_t want = (n_items + wpb - 1) / wpb;
+    const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * occ);
+    kern<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(a);
+    ctx->launches++;
+    CUDA_OK(cudaGetLastError());
+    return SONICS_OK;
+}
+
+int sonics_debug_philox(sonics_ctx *ctx, uint64_t seed, uint64_t sim, uint32_t uid, uint32_t stream_id, int n_blocks,
+                        uint32_t *dev_out)
+{
+    if (!ctx || !dev_out || n_blocks <= 0)
+        return fail(SONICS_ERR_ARG, "sonics_debug_philox: bad argument");
+    CUDA_OK(cudaSetDevice(ctx->device));
+    k_debug_philox<<<1, 1>>>(seed, sim, uid, stream_id, n_blocks, dev_out);
+    ctx->launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaDeviceSynchronize());
+    return SONICS_OK;
+}
+
+int sonics_debug_sample(sonics_ctx *ctx, int kind, int n, double p, int64_t count, uint64_t seed, int32_t *dev_out)
+{
+    if (!ctx || !dev_out || count <= 0 || (kind != 0 && kind != 1))
+        return fail(SONICS_ERR_ARG, "sonics_debug_sample: bad argument");
+    CUDA_OK(cudaSetDevice(ctx->device));
+    k_debug_sample<<<(unsigned)((count + 255) / 256), 256>>>(kind, n, p, count, seed, dev_out);
+    ctx->launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaDeviceSynchronize());
+    return SONICS_OK;
+}
+
+} // extern "C"
+
+#include "abi_stats.inl"

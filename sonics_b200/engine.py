@@ -1,0 +1,199 @@
+"""Host-side engine: owns the C-ABI context and the PyTorch device buffers.
+
+PyTorch is plumbing only (device memory + streams); every computation happens in
+the CUDA library behind include/sonics_b200.h.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _abi
+from ._abi import SonicsParams, SonicsVerdict, check
+
+MAX_ALLELE = 500
+
+VERDICT_DTYPE = np.dtype([
+    ("allele_lo", "<i4"), ("allele_hi", "<i4"), ("filter", "<i4"), ("run_reps", "<i4"), ("min_sim", "<i4"),
+    ("best_sim", "<i4"), ("n_groups", "<i4"), ("p_clamped", "<i4"), ("lnL", "<f8"), ("identity", "<f8"),
+    ("r_squared", "<f8"), ("high_pval", "<f8"), ("best_lnL_ratio", "<f8"), ("percentile_lnL_ratio", "<f8"),
+    ("identity_q75", "<f8"), ("r_squared_q75", "<f8"), ("lnL_q75", "<f8")])
+assert VERDICT_DTYPE.itemsize == ctypes.sizeof(SonicsVerdict)
+
+
+def make_params(n_cycles=24, capture_cycle=13, floor=5, random=False, up_preference=False, start_copies=300000,
+                min_sim=25, monte_carlo=False, down=(0, 0.1), up=(0, 0.1), capture=(-0.25, 0.25),
+                efficiency=(0.001, 0.1), padjust=0.001, lnL_threshold=2.3):
+    """SonicsParams from the reference's CLI defaults (sonics:445-693, 711-751)."""
+    p = SonicsParams()
+    p.n_cycles = int(n_cycles)
+    p.capture_cycle = int(capture_cycle)
+    p.floor_opt = int(floor)
+    p.random_start = int(bool(random))
+    p.up_preference = int(bool(up_preference))
+    p.start_copies = int(start_copies)
+    p.min_sim = int(min_sim)
+    p.monte_carlo = int(bool(monte_carlo))
+    p.down[0], p.down[1] = float(down[0]), float(down[1])
+    p.up[0], p.up[1] = float(up[0]), float(up[1])
+    p.capture[0], p.capture[1] = float(capture[0]), float(capture[1])
+    p.efficiency[0], p.efficiency[1] = float(efficiency[0]), float(efficiency[1])
+    p.padjust = float(padjust)
+    p.lnL_threshold = float(lnL_threshold)
+    return p
+
+
+def params_from_dicts(constants, ranges, options=None):
+    """The reference's `constants` / `ranges` / `options` dicts (sonics:714-751) -> SonicsParams."""
+    options = options or {}
+    return make_params(
+        n_cycles=constants["n_cycles"], capture_cycle=constants["capture_cycle"], floor=constants["floor"],
+        random=constants["random"], up_preference=constants["up_preference"],
+        start_copies=constants["start_copies"], min_sim=options.get("min_sim", 25),
+        monte_carlo=options.get("monte_carlo", False), down=ranges[0], up=ranges[1], capture=ranges[2],
+        efficiency=ranges[3], padjust=constants.get("padjust", 0.001),
+        lnL_threshold=constants.get("lnL_threshold", 2.3))
+
+
+def to_csr(genotypes):
+    """List of reads-per-repeat-count arrays (get_alleles()[0]) -> CSR (allele_off, allele, reads)."""
+    off = np.zeros(len(genotypes) + 1, dtype=np.int32)
+    al, rd = [], []
+    for g, arr in enumerate(genotypes):
+        arr = np.asarray(arr)
+        nz = np.nonzero(arr)[0]
+        al.append(nz.astype(np.int32))
+        rd.append(arr[nz].astype(np.int32))
+        off[g + 1] = off[g] + len(nz)
+    return off, (np.concatenate(al) if al else np.zeros(0, np.int32)), (np.concatenate(rd) if rd else np.zeros(0, np.int32))
+
+
+class Table:
+    """A genotype table resident in device memory (torch uint8 tensor owned here)."""
+
+    def __init__(self, buf, n_gt, allele_off, allele, reads, max_window):
+        self.buf = buf
+        self.n_gt = n_gt
+        self.allele_off = allele_off
+        self.allele = allele
+        self.reads = reads
+        self.max_window = max_window
+
+    def group_label(self, g, gid):
+        """u16 group id -> 'lo/hi' label (sonics.pyx:329-332)."""
+        a0, a1 = self.allele_off[g], self.allele_off[g + 1]
+        A = a1 - a0
+        return "%d/%d" % (self.allele[a0 + gid // A], self.allele[a0 + gid % A])
+
+
+class Engine:
+    def __init__(self, device=0):
+        import torch  # device memory + streams only
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("sonics_b200: no CUDA device visible; this framework has no CPU fallback")
+        self.torch = torch
+        self.lib = _abi.load()
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        torch.cuda.set_device(self.device)
+        torch.zeros(1, device=self.device)  # make sure the primary context exists
+        ctx = ctypes.c_void_p()
+        check(self.lib.sonics_create(self.device_index, ctypes.byref(ctx)))
+        self.ctx = ctx
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.sonics_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers ---------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def sync(self):
+        check(self.lib.sonics_sync(self.ctx, self._stream()))
+
+    @property
+    def launches(self):
+        return int(self.lib.sonics_launch_count(self.ctx))
+
+    # -- test hooks -------------------------------------------------------
+    def debug_philox(self, seed, sim, uid, stream_id, n_blocks):
+        out = self.torch.empty(4 * n_blocks, dtype=self.torch.int32, device=self.device)
+        check(self.lib.sonics_debug_philox(self.ctx, seed, sim, uid, stream_id, n_blocks, out.data_ptr()))
+        return out.cpu().numpy().view(np.uint32)
+
+    def debug_sample(self, kind, n, p, count, seed):
+        out = self.torch.empty(count, dtype=self.torch.int32, device=self.device)
+        check(self.lib.sonics_debug_sample(self.ctx, {"binomial": 0, "poisson": 1}[kind], int(n), float(p), int(count),
+                                           int(seed), out.data_ptr()))
+        return out.cpu().numpy()
+
+    # -- pymc_extracted.mvhyperg ------------------------------------------
+    def mvhyperg(self, x, color):
+        """mvhyperg(x, color) like the f2py routine; accepts one row or a 2-D batch of rows."""
+        x = np.ascontiguousarray(x, dtype=np.int64)
+        color = np.ascontiguousarray(color, dtype=np.int64)
+        single = x.ndim == 1
+        x2, c2 = np.atleast_2d(x), np.atleast_2d(color)
+        n, k = x2.shape
+        out = np.empty(n, dtype=np.float64)
+        scratch = self.torch.empty(n * (2 * k * 8 + 8), dtype=self.torch.uint8, device=self.device)
+        check(self.lib.sonics_mvhyperg(self.ctx, x2.ctypes.data, c2.ctypes.data, k, n, out.ctypes.data,
+                                       scratch.data_ptr(), scratch.numel()))
+        return float(out[0]) if single else out
+
+    # -- genotype table -----------------------------------------------------
+    def build_table(self, params, allele_off, allele, reads, noise_coef=None, uid=None):
+        allele_off = np.ascontiguousarray(allele_off, dtype=np.int32)
+        allele = np.ascontiguousarray(allele, dtype=np.int32)
+        reads = np.ascontiguousarray(reads, dtype=np.int32)
+        n_gt = len(allele_off) - 1
+        nc = None if noise_coef is None else np.ascontiguousarray(noise_coef, dtype=np.float32)
+        ui = None if uid is None else np.ascontiguousarray(uid, dtype=np.uint32)
+        nbytes = self.lib.sonics_table_bytes(n_gt, int(allele_off[-1]))
+        buf = self.torch.empty(max(nbytes, 16), dtype=self.torch.uint8, device=self.device)
+        check(self.lib.sonics_table_build(
+            self.ctx, ctypes.byref(params), n_gt, allele_off.ctypes.data, allele.ctypes.data, reads.ctypes.data,
+            None if nc is None else nc.ctypes.data, None if ui is None else ui.ctypes.data, buf.data_ptr(),
+            buf.numel(), self._stream()))
+        return Table(buf, n_gt, allele_off, allele, reads, self.lib.sonics_table_max_window(self.ctx))
+
+    def build_table_from_arrays(self, params, genotypes, noise_coef=None, uid=None):
+        off, al, rd = to_csr(genotypes)
+        return self.build_table(params, off, al, rd, noise_coef, uid)
+
+    # -- K1 -------------------------------------------------------------------
+    def simulate(self, params, table, sim_count, seed, sim_begin=0, readout=False, simpar=False, out=None,
+                 active=None):
+        """Run simulations [sim_begin, sim_begin+sim_count) for every (active) genotype.
+
+        Returns a dict of device tensors shaped [n_gt, stride]: lnL (f64), group (i16 view of u16) and,
+        with readout=True, identity (f64) / rsq (f32); with simpar=True, simpar [n_gt, stride, 4] (f64)."""
+        t = self.torch
+        stride = sim_begin + sim_count
+        if out is None:
+            out = {"lnL": t.empty((table.n_gt, stride), dtype=t.float64, device=self.device),
+                   "group": t.empty((table.n_gt, stride), dtype=t.int16, device=self.device)}
+            if readout:
+                out["identity"] = t.empty((table.n_gt, stride), dtype=t.float64, device=self.device)
+                out["rsq"] = t.empty((table.n_gt, stride), dtype=t.float32, device=self.device)
+            if simpar:
+                out["simpar"] = t.empty((table.n_gt, stride, 4), dtype=t.float64, device=self.device)
+        stride = out["lnL"].shape[1]
+        act_ptr, n_act = None, table.n_gt
+        if active is not None:
+            act_ptr, n_act = active.data_ptr(), int(active.numel())
+        check(self.lib.sonics_simulate(
+            self.ctx, ctypes.byref(params), table.buf.data_ptr(), table.n_gt, act_ptr, n_act, int(sim_begin),
+            int(sim_count), int(seed) & 0xFFFFFFFFFFFFFFFF, int(stride), out["lnL"].data_ptr(),
+            out["group"].data_ptr(), out["identity"].data_ptr() if "identity" in out else None,
+            out["rsq"].data_ptr() if "rsq" in out else None, out["simpar"].data_ptr() if "simpar" in out else None,
+            self._stream()))
+        return out

@@ -1,0 +1,145 @@
+"""GPU parity tests of K1 (the PCR simulation kernel) against the CPU oracle.
+
+The RNG stream differs from the reference's by design, so parity is distributional:
+per genotype-group two-sample KS tests on lnL (north star: p > 0.01 at >= 1e5
+simulations), sentinel fractions, and group frequencies.  Seeds are fixed, so the
+outcome of each test is deterministic."""
+import os
+
+import numpy as np
+import pytest
+import scipy.stats as st
+
+from oracle import oracle as orc
+from sonics_b200 import engine as eng
+from tests.gpu_util import engine, gpu_lnl_by_group
+from tests.util import CFG1, CFG2, CFG3
+
+pytestmark = pytest.mark.gpu
+
+N_ORACLE = int(os.environ.get("SONICS_KS_ORACLE", "100000" if (os.cpu_count() or 1) >= 16 else "30000"))
+
+
+def test_determinism_and_split_invariance():
+    e = engine()
+    params = eng.make_params()
+    table = e.build_table_from_arrays(params, [orc.parse_reads(CFG2), orc.parse_reads(CFG1)], [0.0, 0.0])
+    a = e.simulate(params, table, 4096, seed=99)
+    b = e.simulate(params, table, 4096, seed=99)
+    c = e.simulate(params, table, 4096, seed=100)
+    e.sync()
+    assert (a["lnL"] == b["lnL"]).all() and (a["group"] == b["group"]).all()
+    assert not (a["lnL"] == c["lnL"]).all()
+    # two half-range launches with odd split == one launch (results keyed by sim index only)
+    out = e.simulate(params, table, 1000, seed=99, sim_begin=0, out={k: v.clone().zero_() for k, v in a.items()})
+    e.simulate(params, table, 4096 - 1000, seed=99, sim_begin=1000, out=out)
+    e.sync()
+    assert (out["lnL"] == a["lnL"]).all() and (out["group"] == a["group"]).all()
+    # the readout uses its own RNG stream: lnL identical with and without it
+    r = e.simulate(params, table, 4096, seed=99, readout=True, simpar=True)
+    e.sync()
+    assert (r["lnL"] == a["lnL"]).all()
+    ident = r["identity"].cpu().numpy()
+    assert ((ident >= 0) & (ident <= 1)).all()
+    sp = r["simpar"].cpu().numpy()
+    assert (sp[..., 0] > 0).all() and (sp[..., 0] < 0.1).all() and (sp[..., 1] < sp[..., 0]).all()
+    assert (sp[..., 2] > -0.25).all() and (sp[..., 2] < 0.25).all()
+    assert (sp[..., 3] > 0.001).all() and (sp[..., 3] < 0.1).all()
+
+
+def test_uid_keys_the_stream_not_the_position():
+    e = engine()
+    params = eng.make_params()
+    off, al, rd = eng.to_csr([orc.parse_reads(CFG1), orc.parse_reads(CFG2), orc.parse_reads(CFG1)])
+    t1 = e.build_table(params, off, al, rd, uid=[10, 11, 12])
+    a = e.simulate(params, t1, 512, seed=5)
+    off2, al2, rd2 = eng.to_csr([orc.parse_reads(CFG1)])
+    t2 = e.build_table(params, off2, al2, rd2, uid=[12])
+    b = e.simulate(params, t2, 512, seed=5)
+    e.sync()
+    assert (a["lnL"][2] == b["lnL"][0]).all()
+    assert not (a["lnL"][0] == a["lnL"][2]).all()
+
+
+def _compare(genotype, noise_coef, n_gpu, seed, okw, pkw, groups=None):
+    e = engine()
+    res, _ = gpu_lnl_by_group(e, genotype, n_gpu, seed, noise_coef=noise_coef, **pkw)
+    reads = orc.parse_reads(genotype)
+    nz = np.nonzero(reads)[0]
+    first = int(np.argmax(reads))
+    # group frequencies: second allele uniform over the non-zero input alleles (sonics.pyx:324)
+    counts = np.array([len(res["%d/%d" % (min(first, a), max(first, a))]) for a in nz])
+    assert st.chisquare(counts).pvalue > 1e-4, counts
+    report = []
+    for a in (groups or nz):
+        lbl = "%d/%d" % (min(first, a), max(first, a))
+        g = res[lbl]
+        cfg = orc.make_cfg(noise_coef=noise_coef, rng_mode=1, with_readout=False, force_second=int(a), **okw)
+        o = orc.run_parallel(cfg, reads, 1000 + int(a), N_ORACLE)["lnL"]
+        sg, so = (g == -999999).mean(), (o == -999999).mean()
+        pooled = (sg * len(g) + so * len(o)) / (len(g) + len(o))
+        z = (sg - so) / max(1e-12, np.sqrt(pooled * (1 - pooled) * (1 / len(g) + 1 / len(o))))
+        ks_all = st.ks_2samp(g, o)
+        gv, ov = g[g > -999999], o[o > -999999]
+        ks_valid = st.ks_2samp(gv, ov) if len(gv) > 50 and len(ov) > 50 else None
+        report.append((lbl, len(g), len(o), sg, so, z, ks_all.pvalue, ks_valid.pvalue if ks_valid else float("nan")))
+    for r in report:
+        print("group %-6s n_gpu=%d n_oracle=%d sentinel gpu=%.4f oracle=%.4f z=%+.2f KS(all) p=%.3f KS(valid) p=%.3f" % r)
+    k = len(report)
+    for lbl, ng, no, sg, so, z, p_all, p_valid in report:
+        assert abs(z) < 4.0, (lbl, sg, so, z)
+        assert p_all > 0.01 / k, (lbl, p_all)
+        assert not (p_valid < 0.01 / k), (lbl, p_valid)
+
+
+def test_ks_cfg1_readme_example():
+    _compare(CFG1, 0.0, 600_000, 1, {}, {})
+
+
+def test_ks_cfg2_eight_alleles():
+    _compare(CFG2, 0.0, 1_600_000, 2, {}, {})
+
+
+def test_ks_noise_and_capture_variants():
+    gt = "9|1;10|54;11|914;12|15"
+    nc = orc.auto_noise_coef(orc.parse_reads(gt))
+    assert nc > 0
+    _compare(gt, nc, 400_000, 3, {}, {})
+
+
+def test_ks_nondefault_options():
+    # below-floor amplification (stale ct path), up_preference, other cycle counts and ranges
+    okw = dict(floor_opt=0, up_preference=True, n_cycles=16, capture_cycle=6, start_copies=100001,
+               down=(0.01, 0.2), up=(0.0, 0.15), capture=(-0.4, 0.4), efficiency=(0.05, 0.5))
+    pkw = dict(floor=0, up_preference=True, n_cycles=16, capture_cycle=6, start_copies=100001,
+               down=(0.01, 0.2), up=(0.0, 0.15), capture=(-0.4, 0.4), efficiency=(0.05, 0.5))
+    _compare(CFG1, 0.0, 600_000, 4, okw, pkw)
+
+
+def test_ks_cfg3_wide_window():
+    nc = orc.auto_noise_coef(orc.parse_reads(CFG3))
+    okw = dict(n_cycles=30, capture_cycle=16)
+    pkw = dict(n_cycles=30, capture_cycle=16)
+    global N_ORACLE
+    keep = N_ORACLE
+    N_ORACLE = max(4000, keep // 10)  # 1316 steps per reaction: keep the CPU side bounded
+    try:
+        _compare(CFG3, nc, 800_000, 5, okw, pkw, groups=[28, 36, 20, 45])
+    finally:
+        N_ORACLE = keep
+
+
+def test_random_start_groups_and_less_than_two_alleles():
+    e = engine()
+    params = eng.make_params(random=True)
+    table = e.build_table_from_arrays(params, [orc.parse_reads(CFG1)], [0.0])
+    out = e.simulate(params, table, 90_000, seed=8)
+    e.sync()
+    grp = out["group"][0].cpu().numpy().view(np.uint16)
+    labels, counts = np.unique(grp, return_counts=True)
+    assert len(labels) == 6  # 3 alleles -> 6 unordered pairs
+    # P(i,i) = 1/9, P(i<j) = 2/9
+    exp = np.array([1 if (g // 3) == (g % 3) else 2 for g in labels]) / 9.0 * 90_000
+    assert st.chisquare(counts, exp).pvalue > 1e-4
+    with pytest.raises(Exception, match="Less then two alleles"):
+        e.build_table_from_arrays(params, [orc.parse_reads("9|100")], [0.0])
