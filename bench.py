@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the SONiCS PCR-stutter Monte-Carlo hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): the single
+locus "5|1;6|1;7|5;8|11;9|20;10|24;11|2;12|1", default CLI constants, fixed-count simulation,
+1e6 simulations per genotype group x 8 groups = 8e6 PCR reactions per step per GPU.
+A step = one pass of the hot path (K1: priors -> PCR cycles -> capture -> lnL) over that batch.
+Under torchrun (N > 1) every rank simulates its own disjoint range of simulation indices of the
+same locus (weak scaling, no collective on the data path); rank 0 prints ONE JSON line.
+
+  value  simulated PCR reactions/s, whole job, inputs resident in HBM, CUDA-event timed
+  e2e    same metric through the public host API (genotype string in host memory -> table build
+         + H2D -> simulate -> lnL/group arrays copied back to pinned host memory)
+  roofline        the HBM view the contract asks for (10 B/reaction of mandatory traffic) --
+                  this path is ALU-issue bound, so its frac is tiny by construction
+  issue_roofline  the bounding roofline: warp instructions issued per second
+                  against 148 SMs x 4 schedulers x SM clock; instructions/reaction come from the
+                  committed ncu capture (profiles/), the rate is measured live
+  cpu_baseline    the reference's own one_repeat() (compiled from /root/reference/sonics.pyx into
+                  oracle/_ref by oracle/build_ref.py) on the box's host cores, bounded sample
+
+--impl reference times that CPU implementation instead (all host cores, bounded sample per step).
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG2 = "5|1;6|1;7|5;8|11;9|20;10|24;11|2;12|1"
+SIMS_PER_STEP = 8_000_000
+BYTES_PER_REACTION = 10  # fp64 lnL + u16 group id written per reaction
+METRIC = "simulated_pcr_reactions_per_s"
+UNIT = "reactions/s"
+
+
+# --------------------------------------------------------------------------- CPU arm
+def _ref_worker(args):
+    n, seed = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+    import numpy as np
+    import sonics as ref  # the compiled reference
+
+    alleles, max_allele, _ = ref.get_alleles(CFG2)
+    constants = dict(random=False, n_cycles=24, capture_cycle=13, up_preference=False, floor=5, lnL_threshold=2.3,
+                     start_copies=300000, genotype=CFG2, padjust=0.001, noise_threshold=0.05,
+                     one_allele_threshold=45, max_allele=max_allele, genotype_total=sum(alleles), alleles=alleles,
+                     noise_coef=0)
+    ranges = ((0, 0.1), (0, 0.1), (-0.25, 0.25), (0.001, 0.1))
+    np.random.seed(seed)
+    t0 = time.perf_counter()
+    for _ in range(n):
+        ref.one_repeat(constants, ranges, 100)
+    return time.perf_counter() - t0
+
+
+def _port_worker(args):
+    n, seed = args
+    from oracle import oracle as orc
+    cfg = orc.make_cfg(rng_mode=0, with_readout=True)
+    t0 = time.perf_counter()
+    orc.run(cfg, orc.parse_reads(CFG2), seed, n)
+    return time.perf_counter() - t0
+
+
+def have_ref():
+    d = os.path.join(ROOT, "oracle", "_ref")
+    return os.path.isdir(d) and any(f.startswith("sonics.") and f.endswith(".so") for f in os.listdir(d))
+
+
+def cpu_sample(kind, per_worker, cores, seed):
+    """Run per_worker one_repeat() calls on each of `cores` processes; returns (reactions, seconds)."""
+    worker = _ref_worker if kind == "reference" else _port_worker
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        pool.map(worker, [(per_worker, seed + i) for i in range(cores)])
+    return per_worker * cores, time.perf_counter() - t0
+
+
+def cpu_baseline(target_s=12.0):
+    kind = "reference" if have_ref() else "port"
+    cores = os.cpu_count() or 1
+    # calibrate on a short run, then size the sample for ~target_s seconds
+    n0 = 40 if kind == "reference" else 200
+    r, s = cpu_sample(kind, n0, cores, 1)
+    per_worker = max(n0, int(n0 * target_s / max(s, 1e-3)))
+    r, s = cpu_sample(kind, per_worker, cores, 100)
+    return {"value": r / s, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d one_repeat() calls of the cfg2 locus on %d processes (%.1f s wall)" % (r, cores, s)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    kind = "reference" if have_ref() else "port"
+    cores = os.cpu_count() or 1
+    per_worker = 60 if kind == "reference" else 300
+    for i in range(args.warmup):
+        cpu_sample(kind, max(4, per_worker // 10), cores, 7 + i)
+    total_r, total_s = 0, 0.0
+    for i in range(args.steps):
+        r, s = cpu_sample(kind, per_worker, cores, 1000 + i)
+        total_r += r
+        total_s += s
+    v = total_r / total_s
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg2 single locus %s, default constants; each step a bounded sample of %d "
+                               "one_repeat() calls (the GPU arm runs %d per step per GPU)" %
+                               (CFG2, per_worker * cores, SIMS_PER_STEP)},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": "%d one_repeat() calls per step on %d processes" % (per_worker * cores, cores)},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def load_inst_per_reaction():
+    p = os.path.join(ROOT, "profiles", "k1_counters.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sims", type=int, default=SIMS_PER_STEP, help="reactions per step per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from sonics_b200 import engine as eng
+    from sonics_b200 import sonics as drop_in
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    e = eng.Engine(local)
+    dev = e.device
+    params = eng.make_params()
+    alleles, _, _ = drop_in.get_alleles(CFG2)
+    n = args.sims
+    table = e.build_table_from_arrays(params, [alleles], [0.0], uid=[0])
+    out = {"lnL": torch.empty((1, n), dtype=torch.float64, device=dev),
+           "group": torch.empty((1, n), dtype=torch.int16, device=dev)}
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    h_lnL = torch.empty((1, n), dtype=torch.float64, pin_memory=True)
+    h_grp = torch.empty((1, n), dtype=torch.int16, pin_memory=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def dev_step(i):
+        # every rank owns the simulation indices [rank*n, (rank+1)*n) of step i's seed
+        return e.simulate(params, table, n, seed=20261019 + i, sim_begin=rank * n, out_offset=0, out=out)
+
+    def e2e_step(i):
+        # public host API: genotype string in host memory -> ... -> lnL/group on the host
+        al, _, _ = drop_in.get_alleles(CFG2)
+        t = e.build_table_from_arrays(params, [al], [0.0], uid=[0])
+        o = e.simulate(params, t, n, seed=777 + i, sim_begin=rank * n, out_offset=0, out=out)
+        h_lnL.copy_(o["lnL"], non_blocking=True)
+        h_grp.copy_(o["group"], non_blocking=True)
+        torch.cuda.synchronize()
+        return t
+
+    # ---- warm-up ----
+    for i in range(max(3, args.warmup)):
+        dev_step(-1 - i)
+    e2e_step(-1)
+    barrier()
+
+    # ---- device-resident timing: K steps, CUDA events on the launching stream, L2 flushed between steps ----
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = e.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        dev_step(i)
+        ev[i][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = e.launches - launches0
+    clk = clocks.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+
+    # ---- end-to-end timing through the host API ----
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        tbl = e2e_step(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = int(tbl.buf.numel())
+    d2h = int(h_lnL.numel() * 8 + h_grp.numel() * 2)
+
+    # sanity: the work was really done (sentinel fraction and group spread of the last step)
+    lnl_host = h_lnL.numpy()[0]
+    frac_sentinel = float((lnl_host == -999999.0).mean())
+    assert 0.05 < frac_sentinel < 0.5 and np.isfinite(lnl_host).all(), frac_sentinel
+
+    times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(times[0]), float(times[1])
+
+    if rank == 0:
+        total = float(n) * world * args.steps
+        value = total / (dev_ms * 1e-3)
+        kernel_ms = dev_ms / args.steps
+        peaks = {}
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        achieved_gbs = n * BYTES_PER_REACTION / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64 lnL / f32+int32 sampling", "data": "synthetic",
+            "config": {"workload": "cfg2: single locus %s, default constants (24 cycles, capture at 13, 300000 start "
+                                   "copies), fixed-count simulation, %d reactions per step per GPU" % (CFG2, n),
+                       "l2": "flushed between steps (256 MiB memset, untimed)", "seed": 20261019},
+            "e2e": {"value": total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved_gbs / hbm_peak, "traffic": None,
+                         "peak_source": "measured" if peaks else "fallback",
+                         "note": "K1 is ALU-issue bound: %d B/reaction of mandatory HBM traffic; see issue_roofline"
+                                 % BYTES_PER_REACTION},
+            "wall_s_timed_region": t_wall,
+            "sentinel_fraction": frac_sentinel,
+        }
+        cnt = load_inst_per_reaction()
+        if cnt:
+            sm_mhz = clk.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+            peak_issue = 148 * 4 * sm_mhz * 1e6  # warp instructions / s at the clock seen during the run
+            ach = cnt["warp_inst_per_reaction"] * n / (kernel_ms * 1e-3)
+            line["roofline"]["traffic"] = cnt.get("dram_bytes_per_launch")
+            line["issue_roofline"] = {
+                "bound": "alu_issue", "achieved": ach, "peak": peak_issue, "unit": "warp-inst/s", "frac": ach / peak_issue,
+                "warp_inst_per_reaction": cnt["warp_inst_per_reaction"], "source": cnt.get("source")}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

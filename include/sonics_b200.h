@@ -130,20 +130,22 @@ int sonics_table_max_window(sonics_ctx *ctx);
 /* ---- K1: fixed-count simulations (one_repeat() x sim_count per genotype) --
  * For every genotype g listed in dev_active (all n_gt when dev_active is NULL)
  * run simulations j = sim_begin .. sim_begin+sim_count-1 (sonics.pyx:293-394
- * incl. simulate() :397-480 and the lnL :360-363) and store
- *   dev_lnL  [g*out_stride + j]   fp64 lnL or SONICS_SENTINEL
- *   dev_group[g*out_stride + j]   u16 group id = lo_idx*n_alleles + hi_idx, the indices (into the
+ * incl. simulate() :397-480 and the lnL :360-363) and store, at
+ * o = g*out_stride + out_offset + (j - sim_begin)  (the repeat-until-pass loop uses out_offset = sim_begin,
+ * i.e. a cumulative per-genotype array; a rank that owns a slice of the index range uses 0),
+ *   dev_lnL  [o]   fp64 lnL or SONICS_SENTINEL
+ *   dev_group[o]   u16 group id = lo_idx*n_alleles + hi_idx, the indices (into the
  *                                 genotype's allele list) of the two start alleles, lo_idx <= hi_idx
  * and, when the pointers are non-NULL,
  *   dev_identity (fp64), dev_rsq (fp32; a C float in the reference, sonics.pyx:300): descriptors of
  *                                 the simulated sequencing readout, sonics.pyx:341-357,365-384
- *   dev_simpar [4*(g*out_stride + j)]   fp64 down, up, capture, efficiency (the report columns :387-393).
+ *   dev_simpar [4*o .. 4*o+3]   fp64 down, up, capture, efficiency (the report columns :387-393).
  * The RNG is Philox4x32-10 keyed by (seed; uid, j): results do not depend on
  * launch geometry, on sim_begin/sim_count splits, or on the GPU that runs them. */
 int sonics_simulate(sonics_ctx *ctx, const SonicsParams *params, const void *dev_table, int n_gt,
                     const int32_t *dev_active, int n_active, int64_t sim_begin, int64_t sim_count, uint64_t seed,
-                    int64_t out_stride, double *dev_lnL, uint16_t *dev_group, double *dev_identity, float *dev_rsq,
-                    double *dev_simpar, void *stream);
+                    int64_t out_stride, int64_t out_offset, double *dev_lnL, uint16_t *dev_group,
+                    double *dev_identity, float *dev_rsq, double *dev_simpar, void *stream);
 
 /* ---- K2/K3: per-genotype statistics on the cumulative lnL arrays ---------
  * Restates sonics.pyx:136-191 (+ :208-252 for the final verdict): grouping,

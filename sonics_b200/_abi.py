@@ -76,8 +76,8 @@ PROTOTYPES = {
     "sonics_table_bytes": (_SZ, [_I, _I]),
     "sonics_table_build": (_I, [_P, ctypes.POINTER(SonicsParams), _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "sonics_table_max_window": (_I, [_P]),
-    "sonics_simulate": (_I, [_P, ctypes.POINTER(SonicsParams), _P, _I, _P, _I, _I64, _I64, _U64, _I64, _P, _P, _P, _P,
-                             _P, _P]),
+    "sonics_simulate": (_I, [_P, ctypes.POINTER(SonicsParams), _P, _I, _P, _I, _I64, _I64, _U64, _I64, _I64, _P, _P,
+                             _P, _P, _P, _P]),
     "sonics_evaluate": (_I, [_P, ctypes.POINTER(SonicsParams), _P, _I, _P, _I, _I64, _I64, _P, _P, _I, _P, _P]),
     "sonics_genotype_work_bytes": (_SZ, [_I, _I, _I]),
     "sonics_genotype_batch": (_I, [_P, ctypes.POINTER(SonicsParams), _I, _P, _P, _P, _P, _P, _I, _U64, _P, _P, _SZ,

@@ -10,6 +10,11 @@
 // so a simulation's draws depend only on (seed, uid, sim index, stream) and
 // never on launch geometry, batch splits, or the GPU that runs it.  That is
 // what lets the replay kernel regenerate the best simulation bit for bit.
+//
+// Consumption is in whole 128-bit blocks requested at warp-convergent points of
+// the kernel (one block serves the proposal pairs of two rejection trials), not
+// through a per-lane buffer: a buffered next() desynchronises the lanes' refill
+// points and the 10-round Philox body then runs at 3-4 active lanes (ncu, r01).
 #pragma once
 #include <stdint.h>
 
@@ -17,8 +22,8 @@ namespace sonics {
 
 enum : uint32_t { STREAM_MAIN = 0u, STREAM_READOUT = 1u };
 
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                              uint32_t k1, uint32_t &o0, uint32_t &o1, uint32_t &o2, uint32_t &o3)
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                               uint32_t k1)
 {
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
@@ -33,17 +38,26 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
         k0 += 0x9E3779B9u;
         k1 += 0xBB67AE85u;
     }
-    o0 = c0;
-    o1 = c1;
-    o2 = c2;
-    o3 = c3;
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// uniform on the open interval from the top 23 bits: (2m+1) * 2^-24, never 0, never 1.
+// Pure ALU (no I2F on the XU pipe): 1.m - (1 - 2^-24).
+__device__ __forceinline__ float u01_open(uint32_t x)
+{
+    return __uint_as_float(0x3f800000u | (x >> 9)) - 0.99999994f;
+}
+// uniform in [0, 1 - 2^-24] with 2^-32 resolution near 0 (inversion samplers)
+__device__ __forceinline__ float u01_fine(uint32_t x) { return __uint2float_rz(x) * 2.3283064365386963e-10f; }
+// 53-bit double in [0,1): same construction as numpy's legacy next_double
+__device__ __forceinline__ double u01_53(uint32_t a, uint32_t b)
+{
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
 }
 
 struct Rng {
     uint32_t k0, k1;
     uint32_t blk, c1, c2, c3;
-    uint32_t b0, b1, b2, b3;
-    int left;
 
     __device__ __forceinline__ void init(uint64_t seed, uint64_t sim, uint32_t uid, uint32_t stream)
     {
@@ -53,35 +67,39 @@ struct Rng {
         c1 = (uint32_t)sim;
         c2 = uid;
         c3 = stream | ((uint32_t)(sim >> 32) << 8);
-        left = 0;
-        b0 = b1 = b2 = b3 = 0u;
     }
-    __device__ __forceinline__ uint32_t next()
+    // the next 4 x 32 random bits of this simulation's stream
+    __device__ __forceinline__ uint4 block4()
     {
-        if (left == 0) {
-            philox4x32_10(blk, c1, c2, c3, k0, k1, b0, b1, b2, b3);
-            ++blk;
-            left = 4;
-        }
-        const uint32_t r = b0;
-        b0 = b1;
-        b1 = b2;
-        b2 = b3;
-        --left;
+        const uint4 r = philox4x32_10(blk, c1, c2, c3, k0, k1);
+        ++blk;
         return r;
     }
-    // uniform on the open interval: (2m+1) * 2^-24, m in [0, 2^23): never 0, never 1
-    __device__ __forceinline__ float uniform_open()
+};
+
+// Hands out (a, b) pairs of 32-bit words: first the pair it was constructed with, then fresh
+// blocks from the stream (two pairs per block).  Used by the rejection samplers for retries.
+struct PairSource {
+    Rng &rng;
+    uint32_t a, b, sa, sb;
+    int spare;
+    __device__ __forceinline__ PairSource(Rng &r, uint32_t a0, uint32_t b0) : rng(r), a(a0), b(b0), sa(0), sb(0), spare(0)
     {
-        return __uint2float_rn(((next() >> 9) << 1) | 1u) * 5.9604644775390625e-08f;
     }
-    // uniform in [0, 1 - 2^-24] with 2^-32 resolution near 0 (inversion samplers)
-    __device__ __forceinline__ float uniform_fine() { return __uint2float_rz(next()) * 2.3283064365386963e-10f; }
-    // 53-bit double in [0,1): same construction as numpy's legacy next_double
-    __device__ __forceinline__ double uniform53()
+    __device__ __forceinline__ void advance()
     {
-        const uint32_t a = next() >> 5, b = next() >> 6;
-        return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+        if (spare) {
+            a = sa;
+            b = sb;
+            spare = 0;
+        } else {
+            const uint4 r = rng.block4();
+            a = r.x;
+            b = r.y;
+            sa = r.z;
+            sb = r.w;
+            spare = 1;
+        }
     }
 };
 

@@ -68,7 +68,7 @@ struct SimArgs {
     int32_t warps_per_gt;
     int64_t sim_begin, sim_count;
     uint64_t seed;
-    int64_t out_stride;
+    int64_t out_stride, out_offset;
     double *lnL;
     uint16_t *group;
     double *identity;
@@ -124,22 +124,37 @@ __global__ void k_debug_philox(uint64_t seed, uint64_t sim, uint32_t uid, uint32
 {
     Rng r;
     r.init(seed, sim, uid, stream_id);
-    for (int i = 0; i < 4 * n_blocks; ++i)
-        out[i] = r.next();
+    for (int i = 0; i < n_blocks; ++i) {
+        const uint4 v = r.block4();
+        out[4 * i + 0] = v.x;
+        out[4 * i + 1] = v.y;
+        out[4 * i + 2] = v.z;
+        out[4 * i + 3] = v.w;
+    }
 }
 
 __global__ void k_debug_sample(int kind, int n, double p, int64_t count, uint64_t seed, int32_t *out)
 {
+    __shared__ float rcp_tab[SONICS_RCP_TABLE];
+    for (int i = threadIdx.x; i < SONICS_RCP_TABLE; i += blockDim.x)
+        rcp_tab[i] = i ? 1.0f / (float)i : 0.0f;
+    __syncthreads();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count)
         return;
     Rng r;
     r.init(seed, (uint64_t)t, 0x5eedu, STREAM_MAIN);
-    out[t] = kind == 0 ? binomial(r, n, (float)p) : poisson(r, p);
+    if (kind == 0) {
+        const uint4 b = r.block4();
+        out[t] = binomial(r, n, (float)p, b.x, b.y, rcp_tab);
+    } else {
+        out[t] = poisson(r, p);
+    }
 }
 
 #define SONICS_FULL 0xffffffffu
 
+// Shared-memory layout of k_simulate: [rcp table: SONICS_RCP_TABLE floats][warp 0 region][warp 1 region]...
 // Shared-memory bytes one warp needs for a window of Wcap bins.
 __host__ __device__ inline size_t warp_smem_bytes(int Wcap)
 {
@@ -155,7 +170,11 @@ __global__ void __launch_bounds__(128) k_simulate(const SimArgs a)
     const int warp = threadIdx.x >> 5;
     const int warps_per_block = blockDim.x >> 5;
     const int Wcap = a.Wcap;
-    unsigned char *wbase = smem_raw + (size_t)warp * warp_smem_bytes(Wcap);
+    float *rcp_tab = reinterpret_cast<float *>(smem_raw);
+    for (int i = threadIdx.x; i < SONICS_RCP_TABLE; i += blockDim.x)
+        rcp_tab[i] = i ? 1.0f / (float)i : 0.0f;
+    __syncthreads();
+    unsigned char *wbase = smem_raw + SONICS_RCP_TABLE * 4 + (size_t)warp * warp_smem_bytes(Wcap);
     int *hist = reinterpret_cast<int *>(wbase) + lane; // column: hist[b * 32]
     int *s_reads = reinterpret_cast<int *>(wbase) + Wcap * 32;
     double *s_fl = reinterpret_cast<double *>(wbase + (size_t)Wcap * 32 * 4 + (size_t)((Wcap + 1) & ~1) * 4);
@@ -190,11 +209,12 @@ __global__ void __launch_bounds__(128) k_simulate(const SimArgs a)
         // ---- generate_params (sonics.pyx:33-45): d, u, c, p in that order ----
         Rng rng;
         rng.init(a.seed, (uint64_t)j, h.uid, STREAM_MAIN);
-        const double par_down = a.p.down_lo + a.p.down_rng * rng.uniform53();
-        const double par_up = a.p.up_preference ? a.p.up_lo + (a.p.up_hi - a.p.up_lo) * rng.uniform53()
-                                                : a.p.up_lo + (par_down - a.p.up_lo) * rng.uniform53();
-        const double par_cap = a.p.cap_lo + a.p.cap_rng * rng.uniform53();
-        const double par_eff = a.p.eff_lo + a.p.eff_rng * rng.uniform53();
+        const uint4 q0 = rng.block4(), q1 = rng.block4(), q2 = rng.block4();
+        const double par_down = a.p.down_lo + a.p.down_rng * u01_53(q0.x, q0.y);
+        const double par_up = a.p.up_preference ? a.p.up_lo + (a.p.up_hi - a.p.up_lo) * u01_53(q0.z, q0.w)
+                                                : a.p.up_lo + (par_down - a.p.up_lo) * u01_53(q0.z, q0.w);
+        const double par_cap = a.p.cap_lo + a.p.cap_rng * u01_53(q1.x, q1.y);
+        const double par_eff = a.p.eff_lo + a.p.eff_rng * u01_53(q1.z, q1.w);
         const float eff = (float)par_eff; // cdef float efficiency, capture (:401)
         const float capture = (float)par_cap;
         const float l_up = log1pf(-(float)par_up);   // ln(1 - up)
@@ -203,11 +223,11 @@ __global__ void __launch_bounds__(128) k_simulate(const SimArgs a)
         // ---- start alleles (:320-332) ----
         int i1, i2;
         if (a.p.random_start) {
-            i1 = (int)__umulhi(rng.next(), (uint32_t)A);
-            i2 = (int)__umulhi(rng.next(), (uint32_t)A);
+            i1 = (int)__umulhi(q2.x, (uint32_t)A);
+            i2 = (int)__umulhi(q2.y, (uint32_t)A);
         } else {
             i1 = h.first_idx;
-            i2 = (int)__umulhi(rng.next(), (uint32_t)A);
+            i2 = (int)__umulhi(q2.x, (uint32_t)A);
         }
         const int b1 = a.t.allele[h.a_off + i1] - lo;
         const int b2 = a.t.allele[h.a_off + i2] - lo;
@@ -285,12 +305,17 @@ __global__ void __launch_bounds__(128) k_simulate(const SimArgs a)
                     const bool stutter = b >= floor_bin;
                     if (stutter)
                         ct = cur;
+                    // random words for the first trial of each chained draw, fetched at a point
+                    // where every lane that visits this bin is active
+                    const uint4 ra = rng.block4();
+                    uint4 rb = make_uint4(0u, 0u, 0u, 0u);
                     float p_slip = 0.0f, p_upn = 0.0f;
                     if (stutter) {
+                        rb = rng.block4();
                         const float al = (float)(lo + b);
                         const float prob_up = -expm1f(al * l_up);
                         const float prob_down = -expm1f(al * l_dn);
-                        p_slip = -expm1f(al * (l_up + l_dn));
+                        p_slip = fmaf(-prob_up, prob_down, prob_up + prob_down); // 1 - (1-pd)(1-pu)
                         p_upn = __fdividef(prob_up, prob_up + prob_down);
                     }
                     int n = ct;
@@ -299,7 +324,9 @@ __global__ void __launch_bounds__(128) k_simulate(const SimArgs a)
                     const int n_stage = stutter ? 3 : 1;
 #pragma unroll 1
                     for (int stage = 0; stage < n_stage; ++stage) {
-                        const int x = binomial(rng, n, p);
+                        const uint32_t ua = stage == 0 ? ra.x : (stage == 1 ? ra.z : rb.x);
+                        const uint32_t ub = stage == 0 ? ra.y : (stage == 1 ? ra.w : rb.y);
+                        const int x = binomial(rng, n, p, ua, ub, rcp_tab);
                         if (stage == 0) {
                             amp = x;
                             p = p_slip;
@@ -352,7 +379,7 @@ __global__ void __launch_bounds__(128) k_simulate(const SimArgs a)
             }
             like = __dsub_rn(like, __dsub_rn(__dsub_rn(factln_dev(T), h.fl_D), factln_dev(T - D)));
         }
-        const int64_t o = (int64_t)g * a.out_stride + j;
+        const int64_t o = (int64_t)g * a.out_stride + a.out_offset + (j - a.sim_begin);
         if (valid) {
             a.lnL[o] = like;
             const int glo = min(i1, i2), ghi = max(i1, i2);
@@ -376,8 +403,10 @@ __global__ void __launch_bounds__(128) k_simulate(const SimArgs a)
             for (int b = wlo; b <= whi; ++b) {
                 const int c = hist[b * 32];
                 int ni = 0;
-                if (c != 0)
-                    ni = binomial(rr, D, (float)((double)c * invT));
+                if (c != 0) {
+                    const uint4 w = rr.block4();
+                    ni = binomial(rr, D, (float)((double)c * invT), w.x, w.y, rcp_tab);
+                }
                 hist[b * 32] = ni;
                 N += ni;
             }
@@ -390,8 +419,10 @@ __global__ void __launch_bounds__(128) k_simulate(const SimArgs a)
                 for (int b = wlo; b <= whi; ++b) {
                     const int ni = hist[b * 32];
                     int xi = 0;
-                    if (ni > 0 && R > 0)
-                        xi = (ni == M) ? R : binomial(rr, R, __fdividef((float)ni, (float)M));
+                    if (ni > 0 && R > 0) {
+                        const uint4 w = rr.block4();
+                        xi = (ni == M) ? R : binomial(rr, R, __fdividef((float)ni, (float)M), w.x, w.y, rcp_tab);
+                    }
                     R -= xi;
                     M -= ni;
                     hist[b * 32] = xi;

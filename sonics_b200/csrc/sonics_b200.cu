@@ -286,8 +286,8 @@ static int find_table(sonics_ctx *ctx, const void *dev_table, int n_gt, TableInf
 
 int sonics_simulate(sonics_ctx *ctx, const SonicsParams *params, const void *dev_table, int n_gt,
                     const int32_t *dev_active, int n_active, int64_t sim_begin, int64_t sim_count, uint64_t seed,
-                    int64_t out_stride, double *dev_lnL, uint16_t *dev_group, double *dev_identity, float *dev_rsq,
-                    double *dev_simpar, void *stream)
+                    int64_t out_stride, int64_t out_offset, double *dev_lnL, uint16_t *dev_group,
+                    double *dev_identity, float *dev_rsq, double *dev_simpar, void *stream)
 {
     if (!ctx || !dev_table || !dev_lnL || !dev_group)
         return fail(SONICS_ERR_ARG, "sonics_simulate: NULL argument");
@@ -295,8 +295,9 @@ int sonics_simulate(sonics_ctx *ctx, const SonicsParams *params, const void *dev
         return rc;
     if (sim_count <= 0 || sim_begin < 0)
         return fail(SONICS_ERR_ARG, "sonics_simulate: bad simulation range");
-    if (out_stride < sim_begin + sim_count)
-        return fail(SONICS_ERR_SPACE, "sonics_simulate: out_stride %lld < sim_begin + sim_count", (long long)out_stride);
+    if (out_offset < 0 || out_stride < out_offset + sim_count)
+        return fail(SONICS_ERR_SPACE, "sonics_simulate: out_stride %lld < out_offset + sim_count",
+                    (long long)out_stride);
     TableInfo ti;
     TableView tv;
     if (int rc = find_table(ctx, dev_table, n_gt, ti, tv))
@@ -319,6 +320,7 @@ int sonics_simulate(sonics_ctx *ctx, const SonicsParams *params, const void *dev
     a.sim_count = sim_count;
     a.seed = seed;
     a.out_stride = out_stride;
+    a.out_offset = out_offset;
     a.lnL = dev_lnL;
     a.group = dev_group;
     a.identity = dev_identity;
@@ -330,7 +332,7 @@ int sonics_simulate(sonics_ctx *ctx, const SonicsParams *params, const void *dev
     int wpb = (int)std::min<size_t>(4, (200 * 1024) / per_warp);
     if (wpb < 1)
         return fail(SONICS_ERR_RANGE, "window of %d bins does not fit shared memory", a.Wcap);
-    const size_t smem = per_warp * wpb;
+    const size_t smem = SONICS_RCP_TABLE * 4 + per_warp * wpb;
     auto kern = readout ? k_simulate<true> : k_simulate<false>;
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;

@@ -171,13 +171,17 @@ class Engine:
 
     # -- K1 -------------------------------------------------------------------
     def simulate(self, params, table, sim_count, seed, sim_begin=0, readout=False, simpar=False, out=None,
-                 active=None):
-        """Run simulations [sim_begin, sim_begin+sim_count) for every (active) genotype.
+                 active=None, out_offset=None):
+        """Run simulations j in [sim_begin, sim_begin+sim_count) for every (active) genotype.
 
-        Returns a dict of device tensors shaped [n_gt, stride]: lnL (f64), group (i16 view of u16) and,
-        with readout=True, identity (f64) / rsq (f32); with simpar=True, simpar [n_gt, stride, 4] (f64)."""
+        Results land at column out_offset + (j - sim_begin); out_offset defaults to sim_begin (cumulative
+        per-genotype arrays).  Returns a dict of device tensors shaped [n_gt, stride]: lnL (f64), group
+        (i16 view of the u16 ids) and, with readout=True, identity (f64) / rsq (f32); with simpar=True,
+        simpar [n_gt, stride, 4] (f64: down, up, capture, efficiency)."""
         t = self.torch
-        stride = sim_begin + sim_count
+        if out_offset is None:
+            out_offset = sim_begin
+        stride = out_offset + sim_count
         if out is None:
             out = {"lnL": t.empty((table.n_gt, stride), dtype=t.float64, device=self.device),
                    "group": t.empty((table.n_gt, stride), dtype=t.int16, device=self.device)}
@@ -192,7 +196,7 @@ class Engine:
             act_ptr, n_act = active.data_ptr(), int(active.numel())
         check(self.lib.sonics_simulate(
             self.ctx, ctypes.byref(params), table.buf.data_ptr(), table.n_gt, act_ptr, n_act, int(sim_begin),
-            int(sim_count), int(seed) & 0xFFFFFFFFFFFFFFFF, int(stride), out["lnL"].data_ptr(),
+            int(sim_count), int(seed) & 0xFFFFFFFFFFFFFFFF, int(stride), int(out_offset), out["lnL"].data_ptr(),
             out["group"].data_ptr(), out["identity"].data_ptr() if "identity" in out else None,
             out["rsq"].data_ptr() if "rsq" in out else None, out["simpar"].data_ptr() if "simpar" in out else None,
             self._stream()))
