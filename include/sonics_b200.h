@@ -37,6 +37,8 @@ extern "C" {
 #define SONICS_ABI_VERSION 1
 #define SONICS_MAX_ALLELE 500      /* get_alleles(): max_allele, sonics.pyx:21 */
 #define SONICS_SENTINEL (-999999.0) /* lnL when reads > pool, sonics.pyx:360-361 */
+#define SONICS_MAX_ADD_RATIOS 8     /* --add_ratios percentiles carried per verdict */
+#define SONICS_STATS_MAX_REPS 8192  /* simulations per genotype the on-chip statistics path holds */
 
 enum {
     SONICS_OK = 0,
@@ -75,6 +77,9 @@ typedef struct SonicsParams {
     double efficiency[2];  /* ranges[3]                                                  */
     double padjust;        /* constants['padjust']                                       */
     double lnL_threshold;  /* constants['lnL_threshold']                                 */
+    int32_t n_add_ratios;  /* options['add_ratios'] split on ';' (sonics.pyx:232-242)    */
+    int32_t _pad;
+    double add_ratios[SONICS_MAX_ADD_RATIOS];
 } SonicsParams;
 
 /* One verdict per genotype: everything monte_carlo() prints (sonics.pyx:254-265). */
@@ -94,6 +99,9 @@ typedef struct SonicsVerdict {
     double percentile_lnL_ratio;
     /* --monte_carlo extras (sonics.pyx:119-131): 75th percentiles within the best group */
     double identity_q75, r_squared_q75, lnL_q75;
+    /* --add_ratios: q(best) - q(second) per requested percentile.  As in the reference the LAST of them
+     * also overwrites percentile_lnL_ratio before FILTER and the output column are produced (:236-238). */
+    double add_ratio[SONICS_MAX_ADD_RATIOS];
 } SonicsVerdict;
 
 int sonics_abi_version(void);
@@ -151,12 +159,22 @@ int sonics_simulate(sonics_ctx *ctx, const SonicsParams *params, const void *dev
  * Restates sonics.pyx:136-191 (+ :208-252 for the final verdict): grouping,
  * min_sim, top-2 groups by max lnL, 75th-percentile difference, one-sided
  * Mann-Whitney U of the best group against every other group with Bonferroni,
- * PASS predicate.  n_run = cumulative simulations per genotype.  final != 0
- * also fills the FILTER bits of a non-passing genotype.  Verdicts are written to
- * dev_verdict[slot]. */
+ * PASS predicate.  n_run = cumulative simulations per genotype (<= SONICS_STATS_MAX_REPS).
+ * final_round != 0 also fills the FILTER bits of a non-passing genotype.  dev_identity / dev_rsq
+ * are only read in --monte_carlo mode (sonics.pyx:115-131) and may be NULL otherwise.
+ * Verdicts are written to dev_verdict[g] (genotype index). */
 int sonics_evaluate(sonics_ctx *ctx, const SonicsParams *params, const void *dev_table, int n_gt,
                     const int32_t *dev_active, int n_active, int64_t n_run, int64_t out_stride, const double *dev_lnL,
-                    const uint16_t *dev_group, int final_round, SonicsVerdict *dev_verdict, void *stream);
+                    const uint16_t *dev_group, const double *dev_identity, const float *dev_rsq, int final_round,
+                    SonicsVerdict *dev_verdict, void *stream);
+
+/* K4: replay simulation dev_verdict[g].best_sim of every listed genotype (same Philox stream, hence
+ * the same PCR pool and lnL) with the sequencing readout switched on, and fill dev_verdict[g].identity
+ * and .r_squared (sonics.pyx:341-357,365-384 for the reported row only).  Genotypes whose best_sim
+ * is negative (no_success) are skipped. */
+int sonics_replay_best(sonics_ctx *ctx, const SonicsParams *params, const void *dev_table, int n_gt,
+                       const int32_t *dev_active, int n_active, uint64_t seed, SonicsVerdict *dev_verdict,
+                       void *stream);
 
 /* ---- the whole repeat-until-pass loop for a batch of genotypes ------------
  * Equivalent of mapping process_one_genotype() -> monte_carlo() over the list

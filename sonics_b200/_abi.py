@@ -35,6 +35,9 @@ class SonicsParams(ctypes.Structure):
         ("efficiency", ctypes.c_double * 2),
         ("padjust", ctypes.c_double),
         ("lnL_threshold", ctypes.c_double),
+        ("n_add_ratios", ctypes.c_int32),
+        ("_pad", ctypes.c_int32),
+        ("add_ratios", ctypes.c_double * 8),
     ]
 
 
@@ -57,6 +60,7 @@ class SonicsVerdict(ctypes.Structure):
         ("identity_q75", ctypes.c_double),
         ("r_squared_q75", ctypes.c_double),
         ("lnL_q75", ctypes.c_double),
+        ("add_ratio", ctypes.c_double * 8),
     ]
 
 
@@ -78,7 +82,8 @@ PROTOTYPES = {
     "sonics_table_max_window": (_I, [_P]),
     "sonics_simulate": (_I, [_P, ctypes.POINTER(SonicsParams), _P, _I, _P, _I, _I64, _I64, _U64, _I64, _I64, _P, _P,
                              _P, _P, _P, _P]),
-    "sonics_evaluate": (_I, [_P, ctypes.POINTER(SonicsParams), _P, _I, _P, _I, _I64, _I64, _P, _P, _I, _P, _P]),
+    "sonics_evaluate": (_I, [_P, ctypes.POINTER(SonicsParams), _P, _I, _P, _I, _I64, _I64, _P, _P, _P, _P, _I, _P, _P]),
+    "sonics_replay_best": (_I, [_P, ctypes.POINTER(SonicsParams), _P, _I, _P, _I, _U64, _P, _P]),
     "sonics_genotype_work_bytes": (_SZ, [_I, _I, _I]),
     "sonics_genotype_batch": (_I, [_P, ctypes.POINTER(SonicsParams), _I, _P, _P, _P, _P, _P, _I, _U64, _P, _P, _SZ,
                                    _P]),

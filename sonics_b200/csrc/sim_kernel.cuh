@@ -75,6 +75,8 @@ struct SimArgs {
     float *rsq;
     double *simpar;
     int32_t Wcap; // histogram rows per warp in shared memory
+    // replay mode (K4): one simulation per genotype, index taken from verdict[g].best_sim
+    SonicsVerdict *replay;
 };
 
 // fl_reads[i] = factln(reads[i]); hdr[g].fl_D = factln(D)
@@ -187,8 +189,14 @@ __global__ void __launch_bounds__(128) k_simulate(const SimArgs a)
         const int g = a.active ? a.active[slot] : slot;
         const GtHeader h = a.t.hdr[g];
         const int W = h.W, lo = h.lo, A = h.n_alleles, D = h.D;
-        const int64_t j = a.sim_begin + (int64_t)wi * 32 + lane;
-        const bool valid = j < a.sim_begin + a.sim_count;
+        int64_t j = a.sim_begin + (int64_t)wi * 32 + lane;
+        bool valid = j < a.sim_begin + a.sim_count;
+        if (a.replay) {
+            j = a.replay[g].best_sim;
+            valid = lane == 0 && j >= 0;
+            if (j < 0)
+                j = 0;
+        }
 
         // ---- stage the genotype (warp-uniform data) ----
         __syncwarp();
@@ -380,7 +388,7 @@ __global__ void __launch_bounds__(128) k_simulate(const SimArgs a)
             like = __dsub_rn(like, __dsub_rn(__dsub_rn(factln_dev(T), h.fl_D), factln_dev(T - D)));
         }
         const int64_t o = (int64_t)g * a.out_stride + a.out_offset + (j - a.sim_begin);
-        if (valid) {
+        if (valid && !a.replay) {
             a.lnL[o] = like;
             const int glo = min(i1, i2), ghi = max(i1, i2);
             a.group[o] = (uint16_t)(glo * A + ghi);
@@ -449,7 +457,12 @@ __global__ void __launch_bounds__(128) k_simulate(const SimArgs a)
                     ss_tot = 1e-16;
                 r2 = (float)(1.0 - (double)ss_res / ss_tot);
             }
-            if (valid) {
+            if (valid && a.replay) {
+                a.replay[g].identity = ident;
+                a.replay[g].r_squared = (double)r2;
+                if (a.replay[g].lnL != like)
+                    a.replay[g].best_sim = -2; // replay diverged from the recorded simulation: surfaced by the host
+            } else if (valid) {
                 if (a.identity)
                     a.identity[o] = ident;
                 if (a.rsq)

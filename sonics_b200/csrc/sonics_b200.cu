@@ -39,7 +39,7 @@ static int fail(int code, const char *fmt, ...)
     } while (0)
 
 struct TableInfo {
-    int n_gt, n_alleles, max_W;
+    int n_gt, n_alleles, max_W, max_A;
     size_t off_allele, off_reads, off_fl;
 };
 
@@ -196,7 +196,7 @@ int sonics_table_build(sonics_ctx *ctx, const SonicsParams *params, int n_gt, co
     GtHeader *hdr = (GtHeader *)host.data();
     int32_t *h_allele = (int32_t *)(host.data() + ti.off_allele);
     int32_t *h_reads = (int32_t *)(host.data() + ti.off_reads);
-    int max_W = 0;
+    int max_W = 0, max_A = 0;
     const int64_t sum0 = 2 * (int64_t)((double)params->start_copies / 2.0);
     for (int g = 0; g < n_gt; ++g) {
         const int a0 = allele_off[g], a1 = allele_off[g + 1], A = a1 - a0;
@@ -249,8 +249,10 @@ int sonics_table_build(sonics_ctx *ctx, const SonicsParams *params, int n_gt, co
         h.in_lo_bin = min_in - lo;
         h.fl_D = 0.0;
         max_W = std::max(max_W, h.W);
+        max_A = std::max(max_A, A);
     }
     ti.max_W = max_W;
+    ti.max_A = max_A;
     CUDA_OK(cudaSetDevice(ctx->device));
     cudaStream_t s = (cudaStream_t)stream;
     CUDA_OK(cudaMemcpyAsync(dev_table, host.data(), host.size(), cudaMemcpyHostToDevice, s));
@@ -281,6 +283,30 @@ static int find_table(sonics_ctx *ctx, const void *dev_table, int n_gt, TableInf
     tv.allele = (const int32_t *)(base + ti.off_allele);
     tv.reads = (const int32_t *)(base + ti.off_reads);
     tv.fl_reads = (const double *)(base + ti.off_fl);
+    return SONICS_OK;
+}
+
+static int launch_simulate(sonics_ctx *ctx, SimArgs &a, const TableInfo &ti, bool readout, int64_t wpg, void *stream)
+{
+    a.Wcap = ti.max_W;
+    a.warps_per_gt = (int32_t)wpg;
+    const size_t per_warp = warp_smem_bytes(a.Wcap);
+    int wpb = (int)std::min<size_t>(4, (200 * 1024) / per_warp);
+    if (wpb < 1)
+        return fail(SONICS_ERR_RANGE, "window of %d bins does not fit shared memory", a.Wcap);
+    const size_t smem = SONICS_RCP_TABLE * 4 + per_warp * wpb;
+    auto kern = readout ? k_simulate<true> : k_simulate<false>;
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
+    if (occ < 1)
+        occ = 1;
+    const int64_t n_items = (int64_t)a.n_active * wpg;
+    const int64_t want = (n_items + wpb - 1) / wpb;
+    const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * occ);
+    kern<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(a);
+    ctx->launches++;
+    CUDA_OK(cudaGetLastError());
     return SONICS_OK;
 }
 
@@ -315,7 +341,6 @@ int sonics_simulate(sonics_ctx *ctx, const SonicsParams *params, const void *dev
     const int64_t wpg = (sim_count + 31) / 32;
     if (wpg > 2147483647LL)
         return fail(SONICS_ERR_RANGE, "sonics_simulate: sim_count too large");
-    a.warps_per_gt = (int32_t)wpg;
     a.sim_begin = sim_begin;
     a.sim_count = sim_count;
     a.seed = seed;
@@ -326,26 +351,9 @@ int sonics_simulate(sonics_ctx *ctx, const SonicsParams *params, const void *dev
     a.identity = dev_identity;
     a.rsq = dev_rsq;
     a.simpar = dev_simpar;
-    a.Wcap = ti.max_W;
+    a.replay = nullptr;
     const bool readout = dev_identity != nullptr || dev_rsq != nullptr;
-    const size_t per_warp = warp_smem_bytes(a.Wcap);
-    int wpb = (int)std::min<size_t>(4, (200 * 1024) / per_warp);
-    if (wpb < 1)
-        return fail(SONICS_ERR_RANGE, "window of %d bins does not fit shared memory", a.Wcap);
-    const size_t smem = SONICS_RCP_TABLE * 4 + per_warp * wpb;
-    auto kern = readout ? k_simulate<true> : k_simulate<false>;
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
-    if (occ < 1)
-        occ = 1;
-    const int64_t n_items = (int64_t)n_active * wpg;
-    const int64_t want = (n_items + wpb - 1) / wpb;
-    const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * occ);
-    kern<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(a);
-    ctx->launches++;
-    CUDA_OK(cudaGetLastError());
-    return SONICS_OK;
+    return launch_simulate(ctx, a, ti, readout, wpg, stream);
 }
 
 int sonics_debug_philox(sonics_ctx *ctx, uint64_t seed, uint64_t sim, uint32_t uid, uint32_t stream_id, int n_blocks,

@@ -16,13 +16,13 @@ VERDICT_DTYPE = np.dtype([
     ("allele_lo", "<i4"), ("allele_hi", "<i4"), ("filter", "<i4"), ("run_reps", "<i4"), ("min_sim", "<i4"),
     ("best_sim", "<i4"), ("n_groups", "<i4"), ("p_clamped", "<i4"), ("lnL", "<f8"), ("identity", "<f8"),
     ("r_squared", "<f8"), ("high_pval", "<f8"), ("best_lnL_ratio", "<f8"), ("percentile_lnL_ratio", "<f8"),
-    ("identity_q75", "<f8"), ("r_squared_q75", "<f8"), ("lnL_q75", "<f8")])
+    ("identity_q75", "<f8"), ("r_squared_q75", "<f8"), ("lnL_q75", "<f8"), ("add_ratio", "<f8", (8,))])
 assert VERDICT_DTYPE.itemsize == ctypes.sizeof(SonicsVerdict)
 
 
 def make_params(n_cycles=24, capture_cycle=13, floor=5, random=False, up_preference=False, start_copies=300000,
                 min_sim=25, monte_carlo=False, down=(0, 0.1), up=(0, 0.1), capture=(-0.25, 0.25),
-                efficiency=(0.001, 0.1), padjust=0.001, lnL_threshold=2.3):
+                efficiency=(0.001, 0.1), padjust=0.001, lnL_threshold=2.3, add_ratios=""):
     """SonicsParams from the reference's CLI defaults (sonics:445-693, 711-751)."""
     p = SonicsParams()
     p.n_cycles = int(n_cycles)
@@ -39,6 +39,12 @@ def make_params(n_cycles=24, capture_cycle=13, floor=5, random=False, up_prefere
     p.efficiency[0], p.efficiency[1] = float(efficiency[0]), float(efficiency[1])
     p.padjust = float(padjust)
     p.lnL_threshold = float(lnL_threshold)
+    qs = [float(x) for x in add_ratios.split(";")] if add_ratios else []  # sonics.pyx:232-235
+    if len(qs) > 8:
+        raise ValueError("at most 8 --add_ratios percentiles are supported")
+    p.n_add_ratios = len(qs)
+    for i, q in enumerate(qs):
+        p.add_ratios[i] = q
     return p
 
 
@@ -51,7 +57,7 @@ def params_from_dicts(constants, ranges, options=None):
         start_copies=constants["start_copies"], min_sim=options.get("min_sim", 25),
         monte_carlo=options.get("monte_carlo", False), down=ranges[0], up=ranges[1], capture=ranges[2],
         efficiency=ranges[3], padjust=constants.get("padjust", 0.001),
-        lnL_threshold=constants.get("lnL_threshold", 2.3))
+        lnL_threshold=constants.get("lnL_threshold", 2.3), add_ratios=options.get("add_ratios", ""))
 
 
 def to_csr(genotypes):
@@ -201,3 +207,59 @@ class Engine:
             out["rsq"].data_ptr() if "rsq" in out else None, out["simpar"].data_ptr() if "simpar" in out else None,
             self._stream()))
         return out
+
+    # -- K2/K3 ------------------------------------------------------------------
+    def evaluate(self, params, table, out, n_run, final_round=True, active=None, verdict=None):
+        """Statistics of sonics.pyx:136-252 over the first n_run simulations of every (active) genotype.
+
+        `out` is the dict simulate() returns (or any dict with device tensors lnL [n_gt, stride] f64 and
+        group [n_gt, stride] i16).  Returns a device uint8 tensor holding SonicsVerdict[n_gt]."""
+        t = self.torch
+        if verdict is None:
+            verdict = t.zeros(table.n_gt * VERDICT_DTYPE.itemsize, dtype=t.uint8, device=self.device)
+        act_ptr, n_act = None, table.n_gt
+        if active is not None:
+            act_ptr, n_act = active.data_ptr(), int(active.numel())
+        check(self.lib.sonics_evaluate(
+            self.ctx, ctypes.byref(params), table.buf.data_ptr(), table.n_gt, act_ptr, n_act, int(n_run),
+            int(out["lnL"].shape[1]), out["lnL"].data_ptr(), out["group"].data_ptr(),
+            out["identity"].data_ptr() if "identity" in out else None,
+            out["rsq"].data_ptr() if "rsq" in out else None, int(bool(final_round)), verdict.data_ptr(),
+            self._stream()))
+        return verdict
+
+    def replay_best(self, params, table, seed, verdict):
+        check(self.lib.sonics_replay_best(self.ctx, ctypes.byref(params), table.buf.data_ptr(), table.n_gt, None,
+                                          table.n_gt, int(seed) & 0xFFFFFFFFFFFFFFFF, verdict.data_ptr(),
+                                          self._stream()))
+        return verdict
+
+    def verdicts_to_host(self, verdict):
+        self.sync()
+        return verdict.cpu().numpy().view(VERDICT_DTYPE)
+
+    # -- the whole repeat-until-pass loop ---------------------------------------
+    def genotype_batch(self, params, allele_off, allele, reads, noise_coef, max_reps, seed, uid=None):
+        """monte_carlo() for a batch of genotypes (host arrays in, host verdicts out)."""
+        allele_off = np.ascontiguousarray(allele_off, dtype=np.int32)
+        allele = np.ascontiguousarray(allele, dtype=np.int32)
+        reads = np.ascontiguousarray(reads, dtype=np.int32)
+        n_gt = len(allele_off) - 1
+        nc = None if noise_coef is None else np.ascontiguousarray(noise_coef, dtype=np.float32)
+        ui = None if uid is None else np.ascontiguousarray(uid, dtype=np.uint32)
+        nbytes = self.lib.sonics_genotype_work_bytes(n_gt, int(allele_off[-1]), int(max_reps))
+        work = self._workspace(nbytes)
+        out = np.zeros(n_gt, dtype=VERDICT_DTYPE)
+        check(self.lib.sonics_genotype_batch(
+            self.ctx, ctypes.byref(params), n_gt, allele_off.ctypes.data, allele.ctypes.data, reads.ctypes.data,
+            None if nc is None else nc.ctypes.data, None if ui is None else ui.ctypes.data, int(max_reps),
+            int(seed) & 0xFFFFFFFFFFFFFFFF, out.ctypes.data, work.data_ptr(), work.numel(), self._stream()))
+        return out
+
+    def _workspace(self, nbytes):
+        w = getattr(self, "_work", None)
+        if w is None or w.numel() < nbytes:
+            self._work = None
+            w = self.torch.empty(int(nbytes), dtype=self.torch.uint8, device=self.device)
+            self._work = w
+        return w

@@ -35,8 +35,8 @@ def test_abi_loads_and_reports_version():
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(_abi.SonicsParams) == 8 * 4 + 10 * 8
-    assert ctypes.sizeof(_abi.SonicsVerdict) == 8 * 4 + 9 * 8
+    assert ctypes.sizeof(_abi.SonicsParams) == 8 * 4 + 10 * 8 + 8 + 8 * 8
+    assert ctypes.sizeof(_abi.SonicsVerdict) == 8 * 4 + 9 * 8 + 8 * 8
 
 
 def test_no_cpu_fallback_without_gpu():
