@@ -1,0 +1,321 @@
+"""Host driver: the reference's CLI script `sonics` (run_sonics / parse_vcf /
+process_one_genotype / main, sonics:160-761) with the per-genotype map replaced by
+one batched GPU call per shard.
+
+What is kept byte-compatible: the flags and defaults (sonics:445-693), the two
+output headers (sonics:174-207), the 0-/1-allele shortcuts and the auto-noise
+rule of process_one_genotype (sonics:353-419), `--strict` handling in the VCF
+parser (sonics:311-334) and the row format (via sonics_b200.sonics.format_row).
+
+What changes: genotypes are gathered first, pre-filtered on the host, then run
+through sonics_genotype_batch in chunks; with --gpus N (or under torchrun) the
+list is split into contiguous shards, one process per GPU, and the rows are
+written once, in input order, by rank 0 (the reference appends from pool workers
+in completion order, sonics:436).
+"""
+import argparse
+import logging
+import os
+import re
+import sys
+
+import numpy as np
+
+from . import sonics as sonics_mod
+
+VERSION = "0.3.0"  # the reference's VERSION file
+
+DESC = ("SONiCS - Stutter mONte Carlo Simulation (B200-native engine). Models independent PCR reactions with "
+        "reaction parameters drawn from weak uniform priors, scores each simulated PCR pool against the input "
+        "readout with a log-likelihood, and calls the genotype with a Mann-Whitney U test and lnL ratios. "
+        "Same interface as kzkedzierska/sonics; the Monte-Carlo engine runs on the GPU.")
+
+HEADER_MC = ["sample", "block", "ref", "genotype", "identity", "identity_75th_percentile", "r_squared",
+             "r_squared_75th_percentile", "lnL", "lnL_75th_percentile", "repeats\n"]
+HEADER = ["sample", "block", "ref", "genotype", "identity", "r_squared", "lnL", "filter", "MWUtes_pval",
+          "best_lnL_ratio", "quartile_lnL_ratio", "repeats", "additional_ratios\n"]
+
+
+def build_parser():
+    p = argparse.ArgumentParser(prog="sonics", description=DESC)
+    p.add_argument("INPUT", type=str,
+                   help="Either: allele composition - number of reads per allele, example: all1|reads;all2|reads "
+                        "or path to a VCF file if run with --vcf_mode option")
+    p.add_argument("-o", "--out_path", type=str, default=".", metavar="out_path")
+    p.add_argument("-n", "--file_name", type=str, default="sonics_out.txt", metavar="file_name")
+    p.add_argument("-p", "--processes", type=int, default=0, metavar="n_processes",
+                   help="Kept for interface compatibility; the GPU engine batches genotypes instead of forking.")
+    p.add_argument("-t", "--strict", type=int, default=1, metavar="n_strict")
+    p.add_argument("-y", "--pcr_cycles", type=int, default=12, metavar="n_pcr_cycles")
+    p.add_argument("-c", "--after_capture", type=int, default=12, metavar="n_after_capture")
+    p.add_argument("-b", "--block", type=str, default="Block", metavar="block_id")
+    p.add_argument("-a", "--name", type=str, default="sample", metavar="sample_name")
+    p.add_argument("-r", "--repetitions", default=1000, type=int, metavar="n_repetitions")
+    p.add_argument("-g", "--padjust", metavar="p_adjust_threshold", type=float, default=0.001)
+    p.add_argument("-i", "--lnL_threshold", metavar="lnL_threshold", type=float, default=2.3)
+    p.add_argument("-s", "--start_copies", default=300000, type=int, metavar="n_star_copies")
+    p.add_argument("-l", "--noise_threshold", default=0.05, type=float, metavar="noise_threshold")
+    p.add_argument("-f", "--floor", type=int, default=5, metavar="n_floor")
+    p.add_argument("--min_sim", type=int, default=25, metavar="min_sim")
+    p.add_argument("-j", "--one_allele", type=int, default=45, metavar="n_one_allele_threshold")
+    p.add_argument("-e", "--efficiency", nargs=2, default=(0.001, 0.1), metavar=("MIN", "MAX"), type=float)
+    p.add_argument("-d", "--down", nargs=2, metavar=("MIN", "MAX"), type=float, default=(0, 0.1))
+    p.add_argument("-u", "--up", nargs=2, metavar=("MIN", "MAX"), type=float, default=(0, 0.1))
+    p.add_argument("-k", "--capture", nargs=2, default=(-0.25, 0.25), type=float, metavar=("MIN", "MAX"))
+    p.add_argument("--add_ratios", default="", type=str, metavar="ratios")
+    p.add_argument("-m", "--vcf_mode", action="store_true", default=False)
+    p.add_argument("--monte_carlo", action="store_true", default=False)
+    p.add_argument("--random", action="store_true")
+    p.add_argument("--save_report", action="store_true", default=False)
+    p.add_argument("--up_preference", action="store_true")
+    p.add_argument("-v", "--verbose", action="store_true")
+    p.add_argument("--version", action="version", version="%(prog)s {}".format(VERSION))
+    # extensions (not in the reference)
+    p.add_argument("--seed", type=int, default=None,
+                   help="Philox seed for a reproducible run (default: fresh entropy, like the reference).")
+    p.add_argument("--gpus", type=int, default=1, help="GPUs of this box to shard the genotype list over.")
+    p.add_argument("--chunk", type=int, default=65536, help="Genotypes per device batch.")
+    return p
+
+
+def dicts_from_args(args):
+    """constants / ranges / sonics_run_options exactly as main() assembles them (sonics:711-751)."""
+    capture_cycle = args.pcr_cycles + 1
+    n_cycles = args.pcr_cycles + args.after_capture
+    constants = {
+        "random": args.random, "n_cycles": n_cycles, "capture_cycle": capture_cycle,
+        "up_preference": args.up_preference, "floor": args.floor, "lnL_threshold": args.lnL_threshold,
+        "start_copies": args.start_copies, "genotype": args.INPUT, "padjust": args.padjust,
+        "noise_threshold": args.noise_threshold, "one_allele_threshold": args.one_allele}
+    ranges = (args.down, args.up, args.capture, args.efficiency)
+    options = {
+        "repetitions": args.repetitions, "out_path": args.out_path, "strict": args.strict,
+        "file_name": args.file_name, "vcf_mode": args.vcf_mode, "name": args.name, "block": args.block,
+        "processes": args.processes, "verbose": bool(args.verbose), "save_report": args.save_report,
+        "monte_carlo": args.monte_carlo, "add_ratios": args.add_ratios, "min_sim": args.min_sim}
+    return constants, ranges, options
+
+
+def parse_vcf(file_path, strict=1, rng=None):
+    """lobSTR VCF -> [(sample, block, ref, 'allele|reads;...'), ...]   (sonics:246-343).
+
+    Alleles are bp offsets from the reference; they become repeat counts offset / len(MOTIF) + REF.
+    Partial repeats: strict 1 drops the allele, strict 2 drops the sample's genotype, strict 0 moves
+    the support to one of the two neighbouring whole alleles at random.  Two reference defects are
+    NOT reproduced: strict 0 indexes the support array by allele value
+    (IndexError on the README's own example) and strict 2 forgets to advance the sample column."""
+    rng = rng or np.random.default_rng()
+    genotypes_list = []
+    regexp_ref = re.compile(".*REF=([0-9.]*);.*")
+    regexp_motif = re.compile(".*MOTIF=([TCGA]*);.*")
+    samples = []
+    with open(file_path, "r") as fh:
+        for line in fh:
+            if line.startswith("#"):
+                if line.startswith("#CHROM"):
+                    samples = line.strip("\n").split("\t")[9:]
+                continue
+            line_list = line.rstrip("\n").split("\t")
+            block_name = line_list[0]
+            info_field = line_list[7]
+            m = regexp_ref.search(info_field)
+            if m is None:
+                raise Exception("There's something wrong with the vcf file, expecting REF in the INFO field "
+                                "in the 8th column.")
+            ref = int(m.group(1).split(".")[0])
+            m = regexp_motif.search(info_field)
+            if m is None:
+                raise Exception("There's something wrong with the vcf file, expecting MOTIF in the INFO field "
+                                "in the 8th column.")
+            motif_length = len(m.group(1))
+            all_reads_loc = line_list[8].split(":").index("ALLREADS")
+            for k, sample in enumerate(samples):
+                try:
+                    gt_string = line_list[9 + k].split(":")[all_reads_loc]
+                except IndexError:
+                    logging.warning("Missing ALLREADS field in the input for block: %s, sample: %s", block_name, sample)
+                    continue
+                gt_list = gt_string.split(";")
+                alleles = np.array([int(f.split("|")[0]) / motif_length + ref for f in gt_list])
+                support = np.array([f.split("|")[1] for f in gt_list], dtype=int)
+                diff = alleles % 1
+                partial = diff != 0
+                if partial.any():
+                    if strict == 2:
+                        logging.warning("Partial repetition of the motif in block: %s sample: %s. Excluding.",
+                                        block_name, sample)
+                        continue
+                    elif strict == 0:
+                        logging.warning("Partial repetition of the motif in block: %s, sample: %s. Adding support "
+                                        "from partial allele to one of the closest allele on random.",
+                                        block_name, sample)
+                        whole = {int(a): i for i, a in enumerate(alleles) if not partial[i]}
+                        extra_a, extra_s = [], []
+                        for i in np.nonzero(partial)[0]:
+                            target = int(np.floor(alleles[i])) + int(rng.integers(0, 2))
+                            if target in whole:
+                                support[whole[target]] += support[i]
+                            else:
+                                whole[target] = len(alleles) + len(extra_a)
+                                extra_a.append(float(target))
+                                extra_s.append(int(support[i]))
+                            support[i] = 0
+                        if extra_a:
+                            alleles = np.concatenate([alleles, extra_a])
+                            support = np.concatenate([support, extra_s])
+                            order = np.argsort(alleles, kind="stable")
+                            alleles, support = alleles[order], support[order]
+                    else:
+                        logging.warning("Partial repetition of the motif in block: %s sample: %s. Excluding allele.",
+                                        block_name, sample)
+                        support[partial] = 0
+                genot = ";".join("%i|%i" % (a, s) for a, s in zip(alleles, support) if s > 0 and a > 0)
+                genotypes_list.append((sample, block_name, ref, genot))
+    return genotypes_list
+
+
+def prefilter(input_tuple, constants, options):
+    """The part of process_one_genotype() that runs before monte_carlo() (sonics:345-419).
+
+    Returns ('skip', None) | ('row', row_string) | ('sim', (alleles, noise_coef))."""
+    name, block, ref, genotype = input_tuple
+    alleles, _, n_alleles = sonics_mod.get_alleles(genotype)
+    total = sum(alleles)
+    if n_alleles == 0:
+        logging.warning("No alleles provided in input, skipping this genotype: %s for sample: %s.", block, name)
+        return "skip", None
+    if n_alleles == 1:
+        if total > constants["one_allele_threshold"]:
+            one_allele = alleles.nonzero()[0][0]
+            if options["monte_carlo"]:
+                # the reference builds this row but never writes it (sonics:364-374 vs :388-398)
+                return "skip", None
+            result = "\t".join(["{}/{}".format(one_allele, one_allele), ".", ".", ".", "no_simulations", ".", ".", ".",
+                                "0", "."])
+            logging.warning("Only one allele provided in input, with read support above the threshold. Including "
+                            "this genotype: %s for sample: %s in the output. The simulation won't be performed and "
+                            "likelihood won't be calculated.", block, name)
+            return "row", result
+        logging.warning("Only one allele provided in input, with read support below the threshold. Skipping this "
+                        "genotype: %s for sample: %s in the output.", block, name)
+        return "skip", None
+    nz = alleles[alleles.nonzero()]
+    frac = np.amin(nz) / total * np.count_nonzero(alleles)
+    noise_frac = frac / (frac + 1)
+    noise_coef = np.amin(nz) / total if noise_frac < constants["noise_threshold"] else 0
+    return "sim", (alleles, float(noise_coef))
+
+
+def shard_bounds(n, world, rank):
+    """Contiguous shard [lo, hi) of n work items for `rank` of `world` (sizes differ by at most one)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def run_batch(work, constants, ranges, options, seed, device=0, chunk=65536, uid_offset=0):
+    """Rows for a list of ('sim', (alleles, noise)) items, in order; uid = global position keys the RNG."""
+    rows = []
+    for c0 in range(0, len(work), chunk):
+        part = work[c0:c0 + chunk]
+        uids = np.arange(uid_offset + c0, uid_offset + c0 + len(part), dtype=np.uint32)
+        r, _ = sonics_mod.monte_carlo_batch([w[0] for w in part], [w[1] for w in part], options["repetitions"],
+                                            constants, ranges, options, seed_value=seed, device=device, uids=uids)
+        rows.extend(r)
+    return rows
+
+
+def run_sonics(feed_in, constants, ranges, options, seed=None, gpus=1, chunk=65536):
+    """run_sonics() of the reference (sonics:160-244) with the genotype loop batched on the GPU(s)."""
+    os.makedirs(options["out_path"], exist_ok=True)
+    out_file_path = os.path.join(options["out_path"], options["file_name"])
+    options["out_file_path"] = out_file_path
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if options["vcf_mode"]:
+        parsed = parse_vcf(feed_in, options["strict"])
+        if not parsed:
+            raise Exception("No valid genotype after parsing VCF file.")
+    else:
+        parsed = [(options["name"], options["block"], ".", feed_in)]
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), "little")
+    # host pre-filters, then one work list for the device
+    kinds = [prefilter(t, constants, options) for t in parsed]
+    sim_idx = [i for i, (k, _) in enumerate(kinds) if k == "sim"]
+    work = [kinds[i][1] for i in sim_idx]
+    if options["save_report"]:
+        # per-genotype path: every simulation record is written (sonics.pyx:110-113, 201-206)
+        rows = []
+        sonics_mod.seed(seed)
+        for i in sim_idx:
+            c = dict(constants, alleles=kinds[i][1][0], noise_coef=kinds[i][1][1])
+            o = dict(options, name=parsed[i][0], block=parsed[i][1])
+            rows.append(sonics_mod.monte_carlo(options["repetitions"], c, ranges, o))
+    elif world > 1:
+        rows = _run_sharded_torchrun(work, constants, ranges, options, seed, rank, world, chunk)
+    elif gpus > 1:
+        rows = _run_sharded_spawn(work, constants, ranges, options, seed, gpus, chunk)
+    else:
+        rows = run_batch(work, constants, ranges, options, seed, 0, chunk)
+    if rank != 0:
+        return
+    sim_rows = dict(zip(sim_idx, rows))
+    with open(out_file_path, "w+") as out_file:
+        out_file.write("\t".join(HEADER_MC if options["monte_carlo"] else HEADER))
+        for i, (name, block, ref, _) in enumerate(parsed):
+            kind, payload = kinds[i]
+            if kind == "skip":
+                continue
+            result = payload if kind == "row" else sim_rows[i]
+            logging.info(result)
+            out_file.write("{}\t{}\t{}\t{}\n".format(name, block, ref, result))
+
+
+def _run_sharded_torchrun(work, constants, ranges, options, seed, rank, world, chunk, batch_fn=None):
+    """One process per GPU under torchrun: contiguous shards, host-side gather to rank 0, no collective
+    on the data path (verdict rows are ~100 B per genotype)."""
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        import torch
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+    lo, hi = shard_bounds(len(work), world, rank)
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    rows = (batch_fn or run_batch)(work[lo:hi], constants, ranges, options, seed, local, chunk, uid_offset=lo)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(rows, gathered, dst=0)
+    if rank != 0:
+        return []
+    return [r for part in gathered for r in part]
+
+
+def _shard_worker(args):
+    work, constants, ranges, options, seed, device, chunk, lo = args
+    return run_batch(work, constants, ranges, options, seed, device, chunk, uid_offset=lo)
+
+
+def _run_sharded_spawn(work, constants, ranges, options, seed, gpus, chunk):
+    """--gpus N from a single command line: one worker process per GPU (spawn), rows gathered in order."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    jobs = []
+    for r in range(gpus):
+        lo, hi = shard_bounds(len(work), gpus, r)
+        jobs.append((work[lo:hi], constants, ranges, options, seed, r, chunk, lo))
+    with ctx.Pool(gpus) as pool:
+        parts = pool.map(_shard_worker, jobs)
+    return [r for part in parts for r in part]
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    logging.basicConfig(level=logging.DEBUG if args.verbose else logging.INFO,
+                        format="%(asctime)s %(levelname)s %(message)s")
+    logging.debug("SONiCS run with the following options:")
+    logging.debug(args)
+    constants, ranges, options = dicts_from_args(args)
+    run_sonics(args.INPUT, constants, ranges, options, seed=args.seed, gpus=args.gpus, chunk=args.chunk)
+
+
+if __name__ == "__main__":
+    main()

@@ -222,6 +222,27 @@ def gen_lnl():
     return {"kats": kats, "spot": spot}
 
 
+VCF_TEXT = """##fileformat=VCFv4.1
+#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tsample1\tsample2\tsample3
+genotype1\t100\t.\tN\t.\t.\t.\tEND=140;MOTIF=TCTA;REF=10;\tGT:ALLREADS\t0/0:-4|1;0|54;4|914;8|15\t0/0:-12|2;-8|22;-4|150;0|1215;4|11\t0/0:0|77
+locus2\t200\t.\tN\t.\t.\t.\tEND=260;MOTIF=AC;REF=14.5;\tGT:ALLREADS\t0/0:-2|30;0|200;2|180;3|7\t0/0:0|40;2|45\t0/0:-6|3;-4|9;0|88;1|2
+locus3\t300\t.\tN\t.\t.\t.\tEND=360;MOTIF=GAT;REF=9;\tGT:DP:ALLREADS\t0/0:9:-3|12;0|130\t0/0:3:0|3\t0/0:9:-9|1;3|5;6|60
+"""
+
+
+def gen_vcf():
+    import importlib.machinery
+    import tempfile
+    cli = importlib.machinery.SourceFileLoader("sonics_cli_ref", "/root/reference/sonics").load_module()
+    with tempfile.NamedTemporaryFile("w", suffix=".vcf", delete=False) as f:
+        f.write(VCF_TEXT)
+        path = f.name
+    out = {"vcf": VCF_TEXT, "strict1": [list(map(lambda x: int(x) if isinstance(x, (int, np.integer)) else x, t))
+                                        for t in cli.parse_vcf(path, 1)]}
+    os.unlink(path)
+    return out
+
+
 def dump(name, obj):
     with open(os.path.join(HERE, name), "w") as f:
         json.dump(obj, f, indent=0, separators=(",", ":"))
@@ -230,7 +251,9 @@ def dump(name, obj):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["rng", "one_repeat", "monte_carlo", "lnl"]
+    which = sys.argv[1:] or ["rng", "one_repeat", "monte_carlo", "lnl", "vcf"]
+    if "vcf" in which:
+        dump("vcf_parse.json", gen_vcf())
     if "rng" in which:
         dump("numpy_legacy_rng.json", gen_rng())
     if "one_repeat" in which:

@@ -1,0 +1,149 @@
+"""CPU tests of the host driver (CLI flags, VCF ingest, pre-filters, sharding, 2-rank gather)."""
+import os
+import subprocess
+import sys
+import tempfile
+import textwrap
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from sonics_b200 import driver, sonics as drop_in
+from tests.util import load
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_get_alleles_contract():
+    a, mx, n = drop_in.get_alleles("8|5;9|113;10|89")
+    assert mx == 500 and n == 3 and a.dtype == np.int64 and a.shape == (500,)
+    assert (a == orc.parse_reads("8|5;9|113;10|89")).all()
+    a, _, n = drop_in.get_alleles("0|7;-3|9;;12|4;")  # alleles <= 0 ignored, empty fields skipped (sonics.pyx:24-27)
+    assert n == 1 and a[12] == 4
+    with pytest.raises(IndexError):
+        drop_in.get_alleles("500|1")
+
+
+def test_cli_defaults_match_reference():
+    """Flags and defaults of the reference's argparse (sonics:445-693)."""
+    a = driver.build_parser().parse_args(["8|5;9|113;10|89"])
+    exp = dict(out_path=".", file_name="sonics_out.txt", processes=0, strict=1, pcr_cycles=12, after_capture=12,
+               block="Block", name="sample", repetitions=1000, padjust=0.001, lnL_threshold=2.3, start_copies=300000,
+               noise_threshold=0.05, floor=5, min_sim=25, one_allele=45, efficiency=(0.001, 0.1), down=(0, 0.1),
+               up=(0, 0.1), capture=(-0.25, 0.25), add_ratios="", vcf_mode=False, monte_carlo=False, random=False,
+               save_report=False, up_preference=False, verbose=False)
+    for k, v in exp.items():
+        assert getattr(a, k) == v, k
+    short = {"-o": "out_path", "-n": "file_name", "-p": "processes", "-t": "strict", "-y": "pcr_cycles",
+             "-c": "after_capture", "-b": "block", "-a": "name", "-r": "repetitions", "-g": "padjust",
+             "-i": "lnL_threshold", "-s": "start_copies", "-l": "noise_threshold", "-f": "floor", "-j": "one_allele"}
+    for flag, dest in short.items():
+        val = "7"
+        b = driver.build_parser().parse_args([flag, val, "x"])
+        assert str(getattr(b, dest)) in ("7", "7.0")
+    constants, ranges, options = driver.dicts_from_args(driver.build_parser().parse_args(["-y", "15", "-c", "15", "x"]))
+    assert constants["n_cycles"] == 30 and constants["capture_cycle"] == 16  # sonics:711-712
+    assert set(constants) == {"random", "n_cycles", "capture_cycle", "up_preference", "floor", "lnL_threshold",
+                              "start_copies", "genotype", "padjust", "noise_threshold", "one_allele_threshold"}
+    assert set(options) == {"repetitions", "out_path", "strict", "file_name", "vcf_mode", "name", "block", "processes",
+                            "verbose", "save_report", "monte_carlo", "add_ratios", "min_sim"}
+    assert len(ranges) == 4
+
+
+def test_parse_vcf_matches_reference():
+    g = load("vcf_parse.json")
+    with tempfile.NamedTemporaryFile("w", suffix=".vcf", delete=False) as f:
+        f.write(g["vcf"])
+    try:
+        got = driver.parse_vcf(f.name, 1)
+        assert [list(t) for t in got] == g["strict1"]
+        # strict 2 drops the sample with a partial repeat, later samples keep their own column
+        got2 = driver.parse_vcf(f.name, 2)
+        assert ("sample2", "locus2", 14, "14|40;15|45") in got2
+        assert not any(t[0] in ("sample1", "sample3") and t[1] == "locus2" for t in got2)
+        # strict 0 moves the partial support (15.5 -> 15 or 16; 14.5 -> 14 or 15)
+        got0 = driver.parse_vcf(f.name, 0, rng=np.random.default_rng(1))
+        s1 = dict(x.split("|") for x in [t for t in got0 if t[:2] == ("sample1", "locus2")][0][3].split(";"))
+        assert sum(int(v) for v in s1.values()) == 30 + 200 + 180 + 7
+    finally:
+        os.unlink(f.name)
+    with tempfile.NamedTemporaryFile("w", suffix=".vcf", delete=False) as f:
+        f.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ts1\nb\t1\t.\tN\t.\t.\t.\tMOTIF=AC;\tGT:ALLREADS\t0/0:0|5\n")
+    try:
+        with pytest.raises(Exception, match="expecting REF"):
+            driver.parse_vcf(f.name, 1)
+    finally:
+        os.unlink(f.name)
+
+
+def test_prefilter_rules():
+    constants = {"one_allele_threshold": 45, "noise_threshold": 0.05}
+    opts = {"monte_carlo": False}
+    assert driver.prefilter(("s", "b", 9, ""), constants, opts) == ("skip", None)
+    assert driver.prefilter(("s", "b", 9, "10|45"), constants, opts) == ("skip", None)  # not above the threshold
+    kind, row = driver.prefilter(("s", "b", 9, "10|46"), constants, opts)
+    assert kind == "row" and row == "10/10\t.\t.\t.\tno_simulations\t.\t.\t.\t0\t."
+    assert driver.prefilter(("s", "b", 9, "10|46"), constants, {"monte_carlo": True}) == ("skip", None)
+    for gt in ("9|1;10|54;11|914;12|15", "8|5;9|113;10|89", "9|100;10|100"):
+        kind, (alleles, nc) = driver.prefilter(("s", "b", 9, gt), constants, opts)
+        assert kind == "sim" and nc == orc.auto_noise_coef(orc.parse_reads(gt))
+
+
+def test_shard_bounds_partition():
+    for n in (0, 1, 7, 8, 1000, 80001):
+        for world in (1, 2, 3, 8):
+            parts = [driver.shard_bounds(n, world, r) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_synthetic_vcf_roundtrip():
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import synth_vcf
+    loci = synth_vcf.make_genotypes(5, 3, seed=3, noisy=0.4)
+    with tempfile.NamedTemporaryFile("w", suffix=".vcf", delete=False) as f:
+        pass
+    try:
+        synth_vcf.write_vcf(f.name, loci, 3)
+        assert driver.parse_vcf(f.name, 1) == synth_vcf.genotype_strings(loci)
+    finally:
+        os.unlink(f.name)
+
+
+WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, %r)
+    import torch.distributed as dist
+    from sonics_b200 import driver
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    work = [("g%%d" %% i, 0.0) for i in range(11)]
+    def fake_batch(part, constants, ranges, options, seed, device, chunk, uid_offset=0):
+        return ["%%s:uid%%d:rank%%d" %% (w[0], uid_offset + k, rank) for k, w in enumerate(part)]
+    rows = driver._run_sharded_torchrun(work, {}, (), {}, 1, rank, world, 4, batch_fn=fake_batch)
+    if rank == 0:
+        assert [r.split(":")[0] for r in rows] == ["g%%d" %% i for i in range(11)], rows
+        assert [r.split(":")[1] for r in rows] == ["uid%%d" %% i for i in range(11)], rows
+        assert rows[0].endswith("rank0") and rows[-1].endswith("rank1")
+        print("GATHER_OK")
+    else:
+        assert rows == []
+    dist.destroy_process_group()
+""")
+
+
+def test_two_rank_gloo_shard_and_gather():
+    """N > 1 host path on CPU: contiguous shards, uid = global position, ordered gather on rank 0."""
+    with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as f:
+        f.write(WORKER % ROOT)
+    try:
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                              "--master-addr", "127.0.0.1", "--master-port", "29631", f.name],
+                             capture_output=True, text=True, timeout=240)
+        assert out.returncode == 0, out.stderr[-2000:]
+        assert "GATHER_OK" in out.stdout
+    finally:
+        os.unlink(f.name)

@@ -1,0 +1,123 @@
+"""GPU end-to-end tests of the `sonics` command line and the genotype/FILTER concordance gate."""
+import os
+import subprocess
+import sys
+import tempfile
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from oracle import stats
+from sonics_b200 import driver
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+def _run_cli(args):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "sonics")] + args, capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    return out
+
+
+def test_cli_string_mode_readme_example():
+    with tempfile.TemporaryDirectory() as d:
+        _run_cli(["8|5;9|113;10|89", "-o", d, "--seed", "1"])
+        lines = open(os.path.join(d, "sonics_out.txt")).read().split("\n")
+        assert lines[0] == ("sample\tblock\tref\tgenotype\tidentity\tr_squared\tlnL\tfilter\tMWUtes_pval\t"
+                            "best_lnL_ratio\tquartile_lnL_ratio\trepeats\tadditional_ratios")
+        f = lines[1].split("\t")
+        assert f[:4] == ["sample", "Block", ".", "9/10"] and f[7] == "PASS" and f[11] in ("100", "500") and f[12] == "."
+        assert lines[2] == ""
+        # --monte_carlo header / row, custom names
+        _run_cli(["8|5;9|113;10|89", "-o", d, "-n", "mc.txt", "--monte_carlo", "-r", "400", "-a", "S", "-b", "B",
+                  "--seed", "2"])
+        lines = open(os.path.join(d, "mc.txt")).read().split("\n")
+        assert lines[0].split("\t")[-1] == "repeats" and len(lines[0].split("\t")) == 11
+        f = lines[1].split("\t")
+        assert f[:4] == ["S", "B", ".", "9/10"] and f[-1] == "400"
+        # same seed -> byte-identical output; --save_report writes every simulation
+        _run_cli(["8|5;9|113;10|89", "-o", d, "-n", "a.txt", "--seed", "5"])
+        _run_cli(["8|5;9|113;10|89", "-o", d, "-n", "b.txt", "--seed", "5"])
+        assert open(os.path.join(d, "a.txt")).read() == open(os.path.join(d, "b.txt")).read()
+        _run_cli(["8|5;9|113;10|89", "-o", d, "-n", "r.txt", "--seed", "5", "--save_report"])
+        rep = open(os.path.join(d, "Block_sample.txt")).read().strip().split("\n")
+        assert rep[0] == "ident\tr_squared\tlnL\tgenotype\tnoise_coef\tdown\tup\tcapture\tefficiency"
+        row = open(os.path.join(d, "r.txt")).read().split("\n")[1].split("\t")
+        assert len(rep) - 1 == int(row[11])
+
+
+def test_cli_vcf_mode_rows_and_order():
+    import synth_vcf
+    loci = synth_vcf.make_genotypes(12, 4, seed=11, cov=(150, 900))
+    with tempfile.TemporaryDirectory() as d:
+        vcf = os.path.join(d, "in.vcf")
+        synth_vcf.write_vcf(vcf, loci, 4)
+        _run_cli(["-m", vcf, "-o", d, "--seed", "3", "--chunk", "7"])
+        rows = [ln.split("\t") for ln in open(os.path.join(d, "sonics_out.txt")).read().strip().split("\n")[1:]]
+        parsed = driver.parse_vcf(vcf, 1)
+        assert [(r[0], r[1], r[2]) for r in rows] == [(p[0], p[1], str(p[2])) for p in parsed]
+        assert all(len(r) == 13 for r in rows)
+        assert sum(r[7] == "PASS" for r in rows) > len(rows) // 2
+        # chunking and the one-batch run give identical files (uid = global position keys the RNG)
+        _run_cli(["-m", vcf, "-o", d, "-n", "one.txt", "--seed", "3"])
+        assert open(os.path.join(d, "one.txt")).read() == open(os.path.join(d, "sonics_out.txt")).read()
+
+
+def _oracle_call(args):
+    reads, noise, seed = args
+    cfg = orc.make_cfg(rng_mode=1, with_readout=False, noise_coef=noise)
+    recs = orc.run(cfg, reads, seed, 1000)
+    pos = [0]
+
+    def draw(n):
+        out = [{"identity": 0.0, "r_squared": 0.0, "lnL": float(r["lnL"]), "label": orc.label(r)}
+               for r in recs[pos[0]:pos[0] + n]]
+        pos[0] += n
+        return out
+    info = stats.monte_carlo(1000, draw)[1]
+    return info["genotype"], info["filter"]
+
+
+def test_concordance_with_oracle_on_synthetic_vcf():
+    """North-star gate (iii), defined as SURVEY.md 7.6 prescribes because both sides are Monte-Carlo:
+    genotype agreement on rows that PASS on both sides >= 99.5 %, and GPU-vs-oracle agreement on
+    (genotype, FILTER) no worse than the oracle's agreement with itself (reported beside it)."""
+    import synth_vcf
+    from sonics_b200 import engine as eng
+    from tests.gpu_util import engine
+    loci = synth_vcf.make_genotypes(60, 4, seed=20261019, cov=(200, 1000))
+    parsed = synth_vcf.genotype_strings(loci)
+    constants = {"one_allele_threshold": 45, "noise_threshold": 0.05}
+    work = []
+    for t in parsed:
+        kind, payload = driver.prefilter(t, constants, {"monte_carlo": False})
+        if kind == "sim":
+            work.append(payload)
+    e = engine()
+    params = eng.make_params()
+    off, al, rd = eng.to_csr([w[0] for w in work])
+    v = e.genotype_batch(params, off, al, rd, [w[1] for w in work], 1000, seed=4242)
+    from sonics_b200.sonics import filter_string
+    gpu = [("%d/%d" % (x["allele_lo"], x["allele_hi"]) if x["allele_lo"] >= 0 else "./.", filter_string(int(x["filter"])))
+           for x in v]
+    with ThreadPoolExecutor(os.cpu_count() or 4) as ex:
+        oa = list(ex.map(_oracle_call, [(w[0], w[1], 100 + i) for i, w in enumerate(work)]))
+        ob = list(ex.map(_oracle_call, [(w[0], w[1], 900000 + i) for i, w in enumerate(work)]))
+    n = len(work)
+
+    def agree(x, y):
+        both = np.mean([a == b for a, b in zip(x, y)])
+        geno = np.mean([a[0] == b[0] for a, b in zip(x, y)])
+        pp = [(a, b) for a, b in zip(x, y) if a[1] == "PASS" and b[1] == "PASS"]
+        return both, geno, np.mean([a[0] == b[0] for a, b in pp]) if pp else 1.0, len(pp)
+    g_o = agree(gpu, oa)
+    o_o = agree(oa, ob)
+    print("n=%d  gpu-vs-oracle: geno+filter %.3f geno %.3f geno|PASS-both %.4f (%d rows)" % ((n,) + g_o))
+    print("      oracle-vs-oracle: geno+filter %.3f geno %.3f geno|PASS-both %.4f (%d rows)" % o_o)
+    assert g_o[2] >= 0.995
+    assert g_o[0] >= o_o[0] - 0.08 and g_o[1] >= o_o[1] - 0.05
