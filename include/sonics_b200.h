@@ -195,6 +195,11 @@ int sonics_genotype_batch(sonics_ctx *ctx, const SonicsParams *params, int n_gt,
  * sonics_debug_sample:  count draws, one per thread (thread t uses sim = t), of
  *      kind 0: Binomial(n, p)    kind 1: Poisson(lam = p)
  * into dev_out (int32).  Both synchronous; dev_out is caller-owned device memory. */
+/* sonics_debug_counters: while dev_counters (16 x u64 of caller-owned device memory, zeroed by the
+ * caller) is non-NULL, sonics_simulate accumulates K1 control-flow statistics into it: [0] passes,
+ * [1..7] lanes per state-machine mode summed over passes, [8] ADVANCE inner trips, [9] lanes entering
+ * ADVANCE, [10] deferred-test executions, [11] lanes served by them, [12] warp work items. */
+int sonics_debug_counters(sonics_ctx *ctx, uint64_t *dev_counters);
 int sonics_debug_philox(sonics_ctx *ctx, uint64_t seed, uint64_t sim, uint32_t uid, uint32_t stream_id, int n_blocks,
                         uint32_t *dev_out);
 int sonics_debug_sample(sonics_ctx *ctx, int kind, int n, double p, int64_t count, uint64_t seed, int32_t *dev_out);

@@ -107,6 +107,7 @@ int sonics_replay_best(sonics_ctx *ctx, const SonicsParams *params, const void *
     a.rsq = nullptr;
     a.simpar = nullptr;
     a.replay = dev_verdict;
+    a.dbg = nullptr;
     return launch_simulate(ctx, a, ti, true, 1, stream);
 }
 

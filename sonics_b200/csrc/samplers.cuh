@@ -38,93 +38,115 @@ __device__ __forceinline__ float stirling_tail(float k)
 // floor(x) for |x| < 2^22 without the XU pipe: round-down add of 1.5 * 2^23
 __device__ __forceinline__ float floor_small(float x) { return __fadd_rd(x, 12582912.0f) - 12582912.0f; }
 
-// Binomial(n, p) for 0 < p <= 0.5 and n*p < 10: inversion by sequential search.
-__device__ __forceinline__ int binomial_inversion(int n, float p, uint32_t bits, const float *rcp_tab)
+// ---- building blocks -------------------------------------------------------------------------
+// The samplers are split into setup / one-trial / deferred-test pieces so that K1's per-lane state
+// machine can interleave them across lanes (one rejection trial or one chunk of inversion steps per
+// pass, the rare Stirling test batched over several lanes).  binomial() below composes the same
+// pieces in lockstep form and is what the exact-pmf tests exercise.
+
+struct InvState { // inversion: Binomial(n, p), p <= 0.5, n*p < 10
+    float u, px, a, s;
+    int x, cap;
+};
+
+__device__ __forceinline__ void inv_setup(InvState &v, int n, float p)
 {
     const float q = 1.0f - p;
-    const float s = __fdividef(p, q);
-    const float a = (float)(n + 1) * s;
-    float px = __expf((float)n * log1pf(-p)); // q^n
-    float u = u01_fine(bits);
-    int x = 0;
-    const int cap = n < SONICS_RCP_TABLE - 1 ? n : SONICS_RCP_TABLE - 1; // P(X > 160 | np < 10) < 1e-130
-    while (u > px && x < cap) {
-        ++x;
-        u -= px;
-        px *= fmaf(a, rcp_tab[x], -s);
+    v.s = __fdividef(p, q);
+    v.a = (float)(n + 1) * v.s;
+    v.px = __expf((float)n * log1pf(-p)); // q^n
+    v.cap = n < SONICS_RCP_TABLE - 1 ? n : SONICS_RCP_TABLE - 1; // P(X > 160 | np < 10) < 1e-130
+    v.x = 0;
+    v.u = 0.0f;
+}
+__device__ __forceinline__ void inv_start(InvState &v, uint32_t bits) { v.u = u01_fine(bits); }
+// up to max_steps steps of the sequential search; true when the draw is finished (result v.x)
+__device__ __forceinline__ bool inv_run(InvState &v, const float *rcp_tab, int max_steps)
+{
+    int k = 0;
+    while (v.u > v.px && v.x < v.cap && k < max_steps) {
+        ++v.x;
+        ++k;
+        v.u -= v.px;
+        v.px *= fmaf(v.a, rcp_tab[v.x], -v.s);
     }
-    return x;
+    return !(v.u > v.px && v.x < v.cap);
 }
 
-// Binomial(n, p) for 0 < p <= 0.5 and n*p >= 10: BTRS + squeeze.
-__device__ __forceinline__ int binomial_btrs(Rng &rng, int n, float p, uint32_t bits_a, uint32_t bits_b)
+struct BtrsState { // BTRS: Binomial(n, p), p <= 0.5, n*p >= 10
+    float fn, p, npq, a, b, vr, alpha, ci, cf, fm;
+    float fk, A; // candidate and ln of the scaled uniform, kept for the deferred test
+};
+
+__device__ __forceinline__ void btrs_setup(BtrsState &s, int n, float p)
 {
-    const float fn = (float)n;
+    s.fn = (float)n;
+    s.p = p;
     const float q = 1.0f - p;
     // n*p exactly as hi + lo (n < 2^24, so fma recovers the rounding error of the product)
-    const float hi = fn * p;
-    const float lo = fmaf(fn, p, -hi);
-    const float npq = hi * q;
-    const float spq = sqrtf(npq);
-    const float b = 1.15f + 2.53f * spq;
-    const float rb = __fdividef(1.0f, b);
-    const float a = -0.0873f + 0.0248f * b + 0.01f * p;
-    const float vr = 0.92f - 4.2f * rb;
-    const float alpha = (2.83f + 5.1f * rb) * spq;
-    const float ci = floorf(hi);               // integer part of n*p (exact in fp32)
-    const float cf = (hi - ci) + lo + 0.5f;    // c = n*p + 0.5 = ci + cf
-    const float fm = ci + floorf(cf - 0.5f + p); // m = floor((n+1) p)
-    PairSource src(rng, bits_a, bits_b);
-    float fk;
-    while (true) {
-        const float u = u01_open(src.a) - 0.5f;
-        const float v = u01_open(src.b);
-        const float us = 0.5f - fabsf(u);
-        const float rus = __fdividef(1.0f, us);
-        // k = floor((2a/us + b) u + c); the fractional work stays below 2^22 in magnitude
-        fk = ci + floor_small(fmaf(fmaf(2.0f * a, rus, b), u, cf));
-        if (us >= 0.07f && v <= vr)
-            break; // quick accept
-        if (fk >= 0.0f && fk <= fn) {
-            const float A = __logf(v * alpha * __fdividef(1.0f, fmaf(a * rus, rus, b)));
-            const float d = fk - fm;
-            const float ad = fabsf(d);
-            bool decided = false, accept = false;
-            if (ad < 0.5f * npq - 1.0f) {
-                // BTPE step 5.2: t - rho <= ln f(k)/f(m) <= t + rho
-                const float rn = __fdividef(1.0f, npq);
-                const float t = -0.5f * d * d * rn;
-                const float rho = (ad * rn) * (fmaf(ad, fmaf(ad, 0.33333333f, 0.625f), 0.16666667f) * rn + 0.5f);
-                // keep a safety margin for the fp32 evaluation of A, t and rho
-                const float eps = 1e-5f * (1.0f + fabsf(t));
-                if (A < t - rho - eps) {
-                    decided = true;
-                    accept = true;
-                } else if (A > t + rho + eps) {
-                    decided = true;
-                }
-            }
-            if (!decided) {
-                // ln f(k)/f(m) with every term conditioned through log1p: each is O(|k-m|)
-                const float r = __fdividef(p, q);
-                const float nk = fn - fk + 1.0f;
-                const float k1 = fk + 1.0f;
-                const float t1 = (fm + 0.5f) * log1pf(-d / k1);
-                const float t2 = (fn - fm + 0.5f) * log1pf(d / nk);
-                const float t3 = d * logf(r * nk / k1);
-                const float h = t1 + t2 + t3 + stirling_tail(fm) + stirling_tail(fn - fm) - stirling_tail(fk) -
-                                stirling_tail(fn - fk);
-                accept = A <= h;
-            }
-            if (accept)
-                break;
-        }
-        src.advance();
-    }
-    return (int)fk;
+    const float hi = s.fn * p;
+    const float lo = fmaf(s.fn, p, -hi);
+    s.npq = hi * q;
+    const float spq = sqrtf(s.npq);
+    s.b = 1.15f + 2.53f * spq;
+    const float rb = __fdividef(1.0f, s.b);
+    s.a = -0.0873f + 0.0248f * s.b + 0.01f * p;
+    s.vr = 0.92f - 4.2f * rb;
+    s.alpha = (2.83f + 5.1f * rb) * spq;
+    s.ci = floorf(hi);                        // integer part of n*p (exact in fp32)
+    s.cf = (hi - s.ci) + lo + 0.5f;           // c = n*p + 0.5 = ci + cf
+    s.fm = s.ci + floorf(s.cf - 0.5f + p);    // m = floor((n+1) p)
 }
 
-// Binomial(n, p), any p in [0, 1].  (bits_a, bits_b): fresh random words for the first trial.
+// One rejection trial.  0 = rejected, 1 = accepted (result s.fk), 2 = undecided: s.fk / s.A hold the
+// candidate for btrs_full().
+__device__ __forceinline__ int btrs_trial(BtrsState &s, uint32_t bits_a, uint32_t bits_b)
+{
+    const float u = u01_open(bits_a) - 0.5f;
+    const float v = u01_open(bits_b);
+    const float us = 0.5f - fabsf(u);
+    const float rus = __fdividef(1.0f, us);
+    // k = floor((2a/us + b) u + c); the fractional work stays below 2^22 in magnitude
+    s.fk = s.ci + floor_small(fmaf(fmaf(2.0f * s.a, rus, s.b), u, s.cf));
+    if (us >= 0.07f && v <= s.vr)
+        return 1; // quick accept
+    if (!(s.fk >= 0.0f && s.fk <= s.fn))
+        return 0;
+    s.A = __logf(v * s.alpha * __fdividef(1.0f, fmaf(s.a * rus, rus, s.b)));
+    const float d = s.fk - s.fm;
+    const float ad = fabsf(d);
+    if (ad < 0.5f * s.npq - 1.0f) {
+        // BTPE step 5.2: t - rho <= ln f(k)/f(m) <= t + rho
+        const float rn = __fdividef(1.0f, s.npq);
+        const float t = -0.5f * d * d * rn;
+        const float rho = (ad * rn) * (fmaf(ad, fmaf(ad, 0.33333333f, 0.625f), 0.16666667f) * rn + 0.5f);
+        const float eps = 1e-5f * (1.0f + fabsf(t)); // margin for the fp32 evaluation of A, t and rho
+        if (s.A < t - rho - eps)
+            return 1;
+        if (s.A > t + rho + eps)
+            return 0;
+    }
+    return 2;
+}
+
+// The exact test for an undecided candidate: A <= ln f(k)/f(m), every term conditioned through
+// log1p so that each is O(|k-m|).
+__device__ __forceinline__ bool btrs_full(const BtrsState &s)
+{
+    const float q = 1.0f - s.p;
+    const float r = __fdividef(s.p, q);
+    const float d = s.fk - s.fm;
+    const float nk = s.fn - s.fk + 1.0f;
+    const float k1 = s.fk + 1.0f;
+    const float t1 = (s.fm + 0.5f) * log1pf(-d / k1);
+    const float t2 = (s.fn - s.fm + 0.5f) * log1pf(d / nk);
+    const float t3 = d * logf(r * nk / k1);
+    const float h = t1 + t2 + t3 + stirling_tail(s.fm) + stirling_tail(s.fn - s.fm) - stirling_tail(s.fk) -
+                    stirling_tail(s.fn - s.fk);
+    return s.A <= h;
+}
+
+// Binomial(n, p), any p in [0, 1], lockstep form.  (bits_a, bits_b): random words for the first trial.
 __device__ __forceinline__ int binomial(Rng &rng, int n, float p, uint32_t bits_a, uint32_t bits_b,
                                         const float *rcp_tab)
 {
@@ -135,57 +157,98 @@ __device__ __forceinline__ int binomial(Rng &rng, int n, float p, uint32_t bits_
     const bool flip = p > 0.5f;
     const float pp = flip ? 1.0f - p : p;
     int k;
-    if ((float)n * pp < 10.0f)
-        k = binomial_inversion(n, pp, bits_a, rcp_tab);
-    else
-        k = binomial_btrs(rng, n, pp, bits_a, bits_b);
+    if ((float)n * pp < 10.0f) {
+        InvState v;
+        inv_setup(v, n, pp);
+        inv_start(v, bits_a);
+        while (!inv_run(v, rcp_tab, 1 << 20))
+            ;
+        k = v.x;
+    } else {
+        BtrsState s;
+        btrs_setup(s, n, pp);
+        PairSource src(rng, bits_a, bits_b);
+        while (true) {
+            const int r = btrs_trial(s, src.a, src.b);
+            if (r == 1 || (r == 2 && btrs_full(s)))
+                break;
+            src.advance();
+        }
+        k = (int)s.fk;
+    }
     return flip ? n - k : k;
 }
 
-// Poisson(lam).  lam arrives as the reference's fp32 `hit` widened to double.  Rare (one draw
-// per non-zero bin per reaction), so the acceptance test simply runs in fp64.
+// ---- Poisson ---------------------------------------------------------------------------------
+// lam arrives as the reference's fp32 `hit` widened to double.  Rare (one draw per non-zero bin per
+// reaction, at the capture cycle), so the acceptance test simply runs in fp64.
+struct PoisState {
+    double lam, loglam;
+    float a, b, invalpha, vr;
+    int k;
+};
+
+// Poisson(lam) for 0 < lam < 10: sequential inversion, run to completion.
+__device__ __forceinline__ int poisson_small(double lam, uint32_t bits)
+{
+    float px = __expf(-(float)lam);
+    float u = u01_fine(bits);
+    const float fl = (float)lam;
+    int x = 0;
+    while (u > px && x < 200) {
+        ++x;
+        u -= px;
+        px *= __fdividef(fl, (float)x);
+    }
+    return x;
+}
+
+__device__ __forceinline__ void pois_setup(PoisState &s, double lam) // lam >= 10: PTRS
+{
+    s.lam = lam;
+    const double slam = sqrt(lam);
+    s.loglam = log(lam);
+    s.b = (float)(0.931 + 2.53 * slam);
+    s.a = -0.059f + 0.02483f * s.b;
+    s.invalpha = 1.1239f + __fdividef(1.1328f, s.b - 3.4f);
+    s.vr = 0.9277f - __fdividef(3.6224f, s.b - 2.0f);
+    s.k = 0;
+}
+
+// One PTRS trial: true = accepted (result s.k)
+__device__ __forceinline__ bool pois_trial(PoisState &s, uint32_t bits_a, uint32_t bits_b)
+{
+    const float u = u01_open(bits_a) - 0.5f;
+    const float v = u01_open(bits_b);
+    const float us = 0.5f - fabsf(u);
+    const double kd = floor((double)(__fdividef(2.0f * s.a, us) + s.b) * (double)u + s.lam + 0.43);
+    s.k = (int)kd;
+    if (us >= 0.07f && v <= s.vr)
+        return true;
+    if (kd < 0.0 || (us < 0.013f && v > us))
+        return false;
+    const double lhs = (double)(__logf(v) + __logf(s.invalpha) - __logf(__fdividef(s.a, us * us) + s.b));
+    const double rhs = -s.lam + kd * s.loglam - lgamma(kd + 1.0);
+    return lhs <= rhs;
+}
+
+// Poisson(lam), lockstep form.
 __device__ __forceinline__ int poisson(Rng &rng, double lam)
 {
     if (!(lam > 0.0))
         return 0;
     const uint4 r0 = rng.block4();
-    if (lam < 10.0) {
-        float px = __expf(-(float)lam);
-        float u = u01_fine(r0.x);
-        const float fl = (float)lam;
-        int x = 0;
-        while (u > px && x < 200) {
-            ++x;
-            u -= px;
-            px *= __fdividef(fl, (float)x);
-        }
-        return x;
-    }
-    const double slam = sqrt(lam);
-    const double loglam = log(lam);
-    const float b = (float)(0.931 + 2.53 * slam);
-    const float a = -0.059f + 0.02483f * b;
-    const float invalpha = 1.1239f + __fdividef(1.1328f, b - 3.4f);
-    const float vr = 0.9277f - __fdividef(3.6224f, b - 2.0f);
+    if (lam < 10.0)
+        return poisson_small(lam, r0.x);
+    PoisState s;
+    pois_setup(s, lam);
     PairSource src(rng, r0.x, r0.y);
     src.sa = r0.z;
     src.sb = r0.w;
     src.spare = 1;
-    while (true) {
-        const float u = u01_open(src.a) - 0.5f;
-        const float v = u01_open(src.b);
-        const float us = 0.5f - fabsf(u);
-        const double kd = floor((double)(__fdividef(2.0f * a, us) + b) * (double)u + lam + 0.43);
-        if (us >= 0.07f && v <= vr)
-            return (int)kd;
-        if (!(kd < 0.0 || (us < 0.013f && v > us))) {
-            const double lhs = (double)(__logf(v) + __logf(invalpha) - __logf(__fdividef(a, us * us) + b));
-            const double rhs = -lam + kd * loglam - lgamma(kd + 1.0);
-            if (lhs <= rhs)
-                return (int)kd;
-        }
+    while (!pois_trial(s, src.a, src.b))
         src.advance();
-    }
+    return s.k;
 }
 
 } // namespace sonics

@@ -6,12 +6,11 @@
 //   simulate          sonics.pyx:397-480  (capture step, amplification / stutter cycles)
 // and the lnL of pymc_extracted.f:63-109 (lnl.cuh).
 //
-// Mapping onto the GPU.  All 32 lanes of a warp simulate the SAME genotype
-// (same reads, same live window), so the genotype description is staged once per
-// warp in shared memory and every loop bound is warp-uniform.  The allele-length
-// histogram of each simulation lives in shared memory as a column
-// hist[bin * 32 + lane] (bank = lane: conflict free); one cycle is one ascending
-// sweep over the live window with the running bin kept in registers:
+// Mapping onto the GPU.  All 32 lanes of a warp simulate the SAME genotype (same reads, same
+// window), so the genotype description is staged once per warp in shared memory.  The
+// allele-length histogram of each simulation lives in shared memory as a column
+// hist[bin * 32 + lane] (bank = lane: conflict free); one cycle is one ascending sweep over the
+// lane's live window with the running bin kept in registers:
 //   raw   = hist[b]             start-of-cycle count  -> "nzp" snapshot  (:424)
 //   cur   = raw + carry         count at visit time, includes the same-cycle
 //                               up-stutter carried in from bin b-1            (:429)
@@ -19,6 +18,21 @@
 //   down-stutter is added to bin b-1, which is still in a register            (:472)
 //   up-stutter becomes `carry` for bin b+1, gated on mol_down > 0 (sic, :473) (:476)
 // so a cycle costs one LDS + one STS per live bin on top of the samplers.
+//
+// Control flow (r01 v3).  The draws of different simulations need different numbers of rejection
+// trials / inversion steps, and ~2 % of the binomial trials need the expensive Stirling test.  In
+// a lockstep formulation every such event stalls the other 31 lanes: ncu measured 7 of 32 lanes
+// active on average.  Here each lane runs its simulation as a small STATE MACHINE and the warp
+// iterates over "passes"; in one pass a lane performs at most one of
+//   ADVANCE   finish the previous draw, walk the sweep to the next non-trivial draw, set it up
+//   INV       up to 8 steps of sequential-search inversion        (n*min(p,q) < 10)
+//   BTRS      one transformed-rejection trial incl. the squeeze   (otherwise)
+//   POIS      one PTRS trial (capture step)
+//   FULL      the Stirling test of an undecided BTRS candidate -- run only when >= 4 lanes wait for
+//             it (or nothing else can progress), so the long path executes with several lanes
+// Lanes drift apart by design; nothing in a lane's stream depends on its neighbours (random words
+// come from the lane's own Philox counter, a fresh 128-bit block every second pass), so results are
+// independent of launch geometry and a single simulation can be replayed bit for bit.
 // Reference quirks reproduced: the stale `ct` of the below-floor branch (:478),
 // the count/index mix in cap_set (:414), fp32 efficiency/capture/hit (:401),
 // up ~ U(up_min, down) (:41), sentinel -999999 (:360-361).
@@ -77,7 +91,11 @@ struct SimArgs {
     int32_t Wcap; // histogram rows per warp in shared memory
     // replay mode (K4): one simulation per genotype, index taken from verdict[g].best_sim
     SonicsVerdict *replay;
+    // optional diagnostics (sonics_debug_counters): 16 x u64, see K1_CNT_* below
+    unsigned long long *dbg;
 };
+enum { K1_CNT_PASSES = 0, K1_CNT_MODE0 = 1 /* .. +6: lanes per mode summed over passes */, K1_CNT_ADV_TRIPS = 8,
+       K1_CNT_ADV_LANES = 9, K1_CNT_FULL_RUNS = 10, K1_CNT_FULL_LANES = 11, K1_CNT_ITEMS = 12 };
 
 // fl_reads[i] = factln(reads[i]); hdr[g].fl_D = factln(D)
 __global__ void k_table_prep(GtHeader *hdr, const int32_t *reads, double *fl_reads, int n_gt, int n_alleles)
@@ -164,6 +182,9 @@ __host__ __device__ inline size_t warp_smem_bytes(int Wcap)
     return (size_t)Wcap * 32 * 4 + (size_t)((Wcap + 1) & ~1) * 4 + (size_t)Wcap * 8;
 }
 
+enum { M_ADV = 0, M_BTRS = 1, M_INV0 = 2, M_INV = 3, M_FULL = 4, M_POIS = 5, M_DONE = 6 };
+enum { PC_CYCLE = 0, PC_CAPSCAN = 1, PC_CAPRESULT = 2, PC_BINSCAN = 3, PC_RESULT = 4, PC_FINISH = 5 };
+
 template <bool READOUT>
 __global__ void __launch_bounds__(128) k_simulate(const SimArgs a)
 {
@@ -227,6 +248,7 @@ __global__ void __launch_bounds__(128) k_simulate(const SimArgs a)
         const float capture = (float)par_cap;
         const float l_up = log1pf(-(float)par_up);   // ln(1 - up)
         const float l_dn = log1pf(-(float)par_down); // ln(1 - down)
+        const float e1_up = expm1f(l_up), e1_dn = expm1f(l_dn); // per-bin step of expm1(al * L)
 
         // ---- start alleles (:320-332) ----
         int i1, i2;
@@ -256,110 +278,281 @@ __global__ void __launch_bounds__(128) k_simulate(const SimArgs a)
                 live_lo = in_lo;
                 live_hi = in_hi;
             }
-        } else { // idle lane of a partially filled warp: empty pool, skips every bin
+        } else { // idle lane of a partially filled warp
             live_lo = W;
             live_hi = -1;
         }
 
-        // ---- simulate (:397-480) ----
-        int ct = 0; // function-scope `ct` of the reference; goes stale below the floor (:478)
+        // ---- simulate (:397-480) as a per-lane state machine ----
         const int floor_bin = h.floor_al - lo;
-        for (int cycle = 1; cycle <= a.p.n_cycles; ++cycle) {
-            const int wlo = __reduce_min_sync(SONICS_FULL, live_lo);
-            const int whi = __reduce_max_sync(SONICS_FULL, live_hi);
-            if (whi < wlo)
-                break; // warp with no valid lane
-            if (cycle == a.p.capture_cycle) {
-                // capture step (:412-423)
-                int maxp = 0, nnz = 0, minidx = -1;
-                for (int b = wlo; b <= whi; ++b) {
-                    const int v = hist[b * 32];
-                    maxp = max(maxp, v);
-                    if (v != 0) {
-                        ++nnz;
-                        if (minidx < 0)
-                            minidx = lo + b;
-                    }
-                }
-                if (nnz > 0) {
-                    const float cap_set = (float)((double)capture / (double)(maxp - minidx));
-                    const float floor_cap =
-                        (float)(1.0 - ((double)__fmul_rn(cap_set, (float)nnz)) / 2.0);
-                    int n = 1;
-                    for (int b = wlo; b <= whi; ++b) {
-                        const int v = hist[b * 32];
-                        if (v != 0) {
-                            ct = v;
-                            const float hit =
-                                __fmul_rn(__fadd_rn(floor_cap, __fmul_rn(cap_set, (float)n)), (float)v);
-                            int k = poisson(rng, (double)hit);
-                            k = k < v ? k : v;
-                            hist[b * 32] = k;
-                            ++n;
-                        }
-                    }
-                }
-            }
-            // amplification sweep (:424-479)
-            const int bend = min(whi + 1, W - 1);
-            int carry = 0;
-            int prev = (wlo > 0) ? hist[(wlo - 1) * 32] : 0; // finished value of bin b-1
-            for (int b = wlo; b <= bend; ++b) {
-                const int raw = hist[b * 32];
-                int cur = raw + carry;
-                carry = 0;
-                int down = 0;
-                if (raw != 0) {
-                    const bool stutter = b >= floor_bin;
-                    if (stutter)
-                        ct = cur;
-                    // random words for the first trial of each chained draw, fetched at a point
-                    // where every lane that visits this bin is active
-                    const uint4 ra = rng.block4();
-                    uint4 rb = make_uint4(0u, 0u, 0u, 0u);
-                    float p_slip = 0.0f, p_upn = 0.0f;
-                    if (stutter) {
-                        rb = rng.block4();
-                        const float al = (float)(lo + b);
-                        const float prob_up = -expm1f(al * l_up);
-                        const float prob_down = -expm1f(al * l_dn);
-                        p_slip = fmaf(-prob_up, prob_down, prob_up + prob_down); // 1 - (1-pd)(1-pu)
-                        p_upn = __fdividef(prob_up, prob_up + prob_down);
-                    }
-                    int n = ct;
-                    float p = eff;
-                    int amp = 0, slip = 0, upn = 0;
-                    const int n_stage = stutter ? 3 : 1;
-#pragma unroll 1
-                    for (int stage = 0; stage < n_stage; ++stage) {
-                        const uint32_t ua = stage == 0 ? ra.x : (stage == 1 ? ra.z : rb.x);
-                        const uint32_t ub = stage == 0 ? ra.y : (stage == 1 ? ra.w : rb.y);
-                        const int x = binomial(rng, n, p, ua, ub, rcp_tab);
+        const int n_cycles = a.p.n_cycles, cap_cycle = a.p.capture_cycle;
+        int mode = valid ? M_ADV : M_DONE;
+        int pc = PC_CYCLE;
+        int cycle = 1;
+        int ct = 0; // function-scope `ct` of the reference; goes stale below the floor (:478)
+        int b = 0, bend = 0, prev = 0, cur = 0, carry = 0, down = 0;
+        int stage = 0, n_stage = 1, amp = 0, slip = 0;
+        float p_slip = 0.0f, p_upn = 0.0f, E_up = 0.0f, E_dn = 0.0f;
+        int x = 0;          // result of the draw that just finished
+        int dn = 0;         // n of the draw in flight
+        bool flip = false;  // draw in flight is on 1 - p
+        bool cap_done = false;
+        int cap_b = 0, cap_hi = 0, cap_n = 1, cap_v = 0;
+        float cap_set = 0.0f, floor_cap = 0.0f;
+        BtrsState bs;
+        InvState iv;
+        PoisState ps;
+
+        unsigned long long c_pass = 0, c_adv_trips = 0, c_adv_lanes = 0, c_full_runs = 0, c_full_lanes = 0;
+        unsigned long long c_mode[7] = {0, 0, 0, 0, 0, 0, 0};
+        while (true) {
+            // ================= ADVANCE =================
+            if (a.dbg)
+                c_adv_lanes += __popc(__ballot_sync(SONICS_FULL, mode == M_ADV));
+            if (mode == M_ADV) {
+                int req = 0; // 1: binomial(dn, dp)   2: poisson(lam)
+                float dp = 0.0f;
+                double lam = 0.0;
+                while (req == 0 && mode == M_ADV) {
+                    if (a.dbg && lane == (__ffs(__activemask()) - 1))
+                        ++c_adv_trips;
+                    if (pc == PC_RESULT) {
                         if (stage == 0) {
                             amp = x;
-                            p = p_slip;
+                            if (n_stage == 1) { // below the floor: plain amplification (:477-479)
+                                cur += amp;
+                                down = 0;
+                                pc = PC_FINISH;
+                            } else {
+                                stage = 1;
+                                dn = amp;
+                                dp = p_slip;
+                                req = 1;
+                            }
                         } else if (stage == 1) {
                             slip = x;
-                            p = p_upn;
+                            stage = 2;
+                            dn = slip;
+                            dp = p_upn;
+                            req = 1;
                         } else {
-                            upn = x;
+                            down = slip - x; // mol_down = mol_slip - mol_up
+                            cur += amp - slip;
+                            if (down > 0)
+                                carry = x; // sic: up-stutter only lands when mol_down > 0 (:473-476)
+                            pc = PC_FINISH;
                         }
-                        n = x;
+                    } else if (pc == PC_FINISH) {
+                        if (b > 0)
+                            hist[(b - 1) * 32] = prev + down;
+                        if (down > 0 && b - 1 < live_lo)
+                            live_lo = b - 1;
+                        if (cur != 0 && b > live_hi)
+                            live_hi = b;
+                        prev = cur;
+                        down = 0;
+                        ++b;
+                        E_up = fmaf(E_up + 1.0f, e1_up, E_up); // expm1((al+1) L) from expm1(al L)
+                        E_dn = fmaf(E_dn + 1.0f, e1_dn, E_dn);
+                        pc = PC_BINSCAN;
+                    } else if (pc == PC_BINSCAN) {
+                        if (b > bend) {
+                            hist[bend * 32] = prev;
+                            ++cycle;
+                            pc = PC_CYCLE;
+                        } else {
+                            const int raw = hist[b * 32];
+                            cur = raw + carry;
+                            carry = 0;
+                            if (raw != 0) { // in the start-of-cycle snapshot (:424)
+                                const bool stutter = b >= floor_bin;
+                                if (stutter) {
+                                    ct = cur;
+                                    const float prob_up = -E_up, prob_down = -E_dn;
+                                    p_slip = fmaf(-prob_up, prob_down, prob_up + prob_down); // 1-(1-pd)(1-pu)
+                                    p_upn = __fdividef(prob_up, prob_up + prob_down);
+                                }
+                                n_stage = stutter ? 3 : 1;
+                                stage = 0;
+                                dn = ct;
+                                dp = eff;
+                                req = 1;
+                                pc = PC_RESULT;
+                            } else {
+                                pc = PC_FINISH;
+                            }
+                        }
+                    } else if (pc == PC_CYCLE) {
+                        if (cycle > n_cycles) {
+                            mode = M_DONE;
+                        } else if (cycle == cap_cycle && !cap_done) {
+                            // capture step (:412-423): max count, first non-zero allele, non-zero count
+                            int maxp = 0, nnz = 0, minidx = -1;
+                            for (int c = live_lo; c <= live_hi; ++c) {
+                                const int v = hist[c * 32];
+                                maxp = max(maxp, v);
+                                if (v != 0) {
+                                    ++nnz;
+                                    if (minidx < 0)
+                                        minidx = lo + c;
+                                }
+                            }
+                            cap_done = true;
+                            if (nnz > 0) {
+                                cap_set = (float)((double)capture / (double)(maxp - minidx));
+                                floor_cap = (float)(1.0 - ((double)__fmul_rn(cap_set, (float)nnz)) / 2.0);
+                                cap_n = 1;
+                                cap_b = live_lo;
+                                cap_hi = live_hi;
+                                pc = PC_CAPSCAN;
+                            }
+                        } else {
+                            // begin the amplification sweep (:424-479)
+                            b = live_lo;
+                            bend = min(live_hi + 1, W - 1);
+                            carry = 0;
+                            down = 0;
+                            prev = b > 0 ? hist[(b - 1) * 32] : 0;
+                            const float al = (float)(lo + b);
+                            E_up = expm1f(al * l_up);
+                            E_dn = expm1f(al * l_dn);
+                            pc = PC_BINSCAN;
+                        }
+                    } else if (pc == PC_CAPSCAN) {
+                        if (cap_b > cap_hi) {
+                            pc = PC_CYCLE;
+                        } else {
+                            cap_v = hist[cap_b * 32];
+                            if (cap_v != 0) {
+                                ct = cap_v;
+                                const float hit = __fmul_rn(
+                                    __fadd_rn(floor_cap, __fmul_rn(cap_set, (float)cap_n)), (float)cap_v);
+                                lam = (double)hit;
+                                pc = PC_CAPRESULT;
+                                if (lam > 0.0)
+                                    req = 2;
+                                else
+                                    x = 0;
+                            } else {
+                                ++cap_b;
+                            }
+                        }
+                    } else { // PC_CAPRESULT
+                        hist[cap_b * 32] = x < cap_v ? x : cap_v;
+                        ++cap_n;
+                        ++cap_b;
+                        pc = PC_CAPSCAN;
                     }
-                    down = slip - upn;
-                    cur += amp - slip;
-                    if (down > 0)
-                        carry = upn; // sic: up-stutter only lands when mol_down > 0 (:473-476)
+                    if (req == 1) { // trivial draws never leave ADVANCE
+                        if (dn <= 0 || !(dp > 0.0f)) {
+                            x = 0;
+                            req = 0;
+                        } else if (dp >= 1.0f) {
+                            x = dn;
+                            req = 0;
+                        }
+                    }
                 }
-                if (b > 0)
-                    hist[(b - 1) * 32] = prev + down;
-                if (down > 0 && b - 1 < live_lo)
-                    live_lo = b - 1;
-                if (cur != 0 && b > live_hi)
-                    live_hi = b;
-                prev = cur;
+                // ---- set the draw up (every lane that leaves ADVANCE with a request is here) ----
+                if (req == 1) {
+                    flip = dp > 0.5f;
+                    const float pp = flip ? 1.0f - dp : dp;
+                    if ((float)dn * pp < 10.0f) {
+                        inv_setup(iv, dn, pp);
+                        mode = M_INV0;
+                    } else {
+                        btrs_setup(bs, dn, pp);
+                        mode = M_BTRS;
+                    }
+                } else if (req == 2) {
+                    pois_setup(ps, lam);
+                    mode = M_POIS;
+                }
             }
-            hist[bend * 32] = prev;
+            if (__all_sync(SONICS_FULL, mode == M_DONE))
+                break;
+            if (a.dbg) {
+                ++c_pass;
+#pragma unroll
+                for (int mm = 0; mm < 7; ++mm)
+                    c_mode[mm] += __popc(__ballot_sync(SONICS_FULL, mode == mm));
+            }
+
+            // ================= one step of the draw in flight =================
+            // A lane that starts an inversion or runs a rejection trial in this pass takes the next
+            // 128-bit block of ITS OWN stream (the block counter advances only when the lane consumes,
+            // never with the warp's pass count: a lane's words must not depend on how long it waited
+            // for its neighbours).  Both pairs are used within the pass: the second one feeds an
+            // immediate retry when the first trial is rejected outright.
+            if (mode == M_INV0 || mode == M_BTRS || mode == M_POIS) {
+                const uint4 words = rng.block4();
+                if (mode == M_INV0) {
+                    inv_start(iv, words.x);
+                    mode = M_INV;
+                } else if (mode == M_BTRS) {
+                    int r = btrs_trial(bs, words.x, words.y);
+                    if (r == 0)
+                        r = btrs_trial(bs, words.z, words.w);
+                    if (r == 1) {
+                        const int k = (int)bs.fk;
+                        x = flip ? dn - k : k;
+                        mode = M_ADV;
+                    } else if (r == 2) {
+                        mode = M_FULL;
+                    }
+                } else {
+                    if (ps.lam < 10.0) {
+                        x = poisson_small(ps.lam, words.x);
+                        mode = M_ADV;
+                    } else if (pois_trial(ps, words.x, words.y) || pois_trial(ps, words.z, words.w)) {
+                        x = ps.k;
+                        mode = M_ADV;
+                    }
+                }
+            }
+            if (mode == M_INV) {
+                if (inv_run(iv, rcp_tab, 8)) {
+                    x = flip ? dn - iv.x : iv.x;
+                    mode = M_ADV;
+                }
+            }
+
+            // ================= deferred Stirling test =================
+            {
+                const unsigned m_full = __ballot_sync(SONICS_FULL, mode == M_FULL);
+                const unsigned m_idle = __ballot_sync(SONICS_FULL, mode == M_FULL || mode == M_DONE);
+                if (__popc(m_full) >= 4 || (m_full != 0u && m_idle == SONICS_FULL)) {
+                    if (a.dbg) {
+                        ++c_full_runs;
+                        c_full_lanes += __popc(m_full);
+                    }
+                    if (mode == M_FULL) {
+                        if (btrs_full(bs)) {
+                            const int k = (int)bs.fk;
+                            x = flip ? dn - k : k;
+                            mode = M_ADV;
+                        } else {
+                            mode = M_BTRS;
+                        }
+                    }
+                }
+            }
+        }
+
+        if (a.dbg) {
+            // c_adv_trips was counted by whichever lane led each trip: sum over the warp
+            for (int o = 16; o > 0; o >>= 1)
+                c_adv_trips += __shfl_down_sync(SONICS_FULL, c_adv_trips, o);
+            if (lane == 0) {
+                atomicAdd(&a.dbg[K1_CNT_PASSES], c_pass);
+                for (int mm = 0; mm < 7; ++mm)
+                    atomicAdd(&a.dbg[K1_CNT_MODE0 + mm], c_mode[mm]);
+                atomicAdd(&a.dbg[K1_CNT_ADV_TRIPS], c_adv_trips);
+                atomicAdd(&a.dbg[K1_CNT_ADV_LANES], c_adv_lanes);
+                atomicAdd(&a.dbg[K1_CNT_FULL_RUNS], c_full_runs);
+                atomicAdd(&a.dbg[K1_CNT_FULL_LANES], c_full_lanes);
+                atomicAdd(&a.dbg[K1_CNT_ITEMS], 1ull);
+            }
         }
 
         // ---- lnL (:360-363, pymc_extracted.f:88-108) ----

@@ -48,6 +48,7 @@ struct sonics_ctx {
     int sm_count;
     int64_t launches;
     int max_W_last;
+    unsigned long long *dbg;
     std::map<const void *, TableInfo> tables;
 };
 
@@ -89,6 +90,7 @@ int sonics_create(int device, sonics_ctx **out)
     c->sm_count = prop.multiProcessorCount;
     c->launches = 0;
     c->max_W_last = 0;
+    c->dbg = nullptr;
     *out = c;
     return SONICS_OK;
 }
@@ -352,8 +354,17 @@ int sonics_simulate(sonics_ctx *ctx, const SonicsParams *params, const void *dev
     a.rsq = dev_rsq;
     a.simpar = dev_simpar;
     a.replay = nullptr;
+    a.dbg = ctx->dbg;
     const bool readout = dev_identity != nullptr || dev_rsq != nullptr;
     return launch_simulate(ctx, a, ti, readout, wpg, stream);
+}
+
+int sonics_debug_counters(sonics_ctx *ctx, uint64_t *dev_counters)
+{
+    if (!ctx)
+        return fail(SONICS_ERR_ARG, "sonics_debug_counters: ctx is NULL");
+    ctx->dbg = (unsigned long long *)dev_counters;
+    return SONICS_OK;
 }
 
 int sonics_debug_philox(sonics_ctx *ctx, uint64_t seed, uint64_t sim, uint32_t uid, uint32_t stream_id, int n_blocks,
