@@ -153,20 +153,30 @@ int sonics_table_max_window(sonics_ctx *ctx);
 int sonics_simulate(sonics_ctx *ctx, const SonicsParams *params, const void *dev_table, int n_gt,
                     const int32_t *dev_active, int n_active, int64_t sim_begin, int64_t sim_count, uint64_t seed,
                     int64_t out_stride, int64_t out_offset, double *dev_lnL, uint16_t *dev_group,
-                    double *dev_identity, float *dev_rsq, double *dev_simpar, void *stream);
+                    double *dev_identity, float *dev_rsq, double *dev_simpar, void *dev_scratch,
+                    size_t dev_scratch_bytes, void *stream);
+/* Scratch for sonics_simulate / sonics_replay_best: the final PCR pools of the work units of one chunk
+ * (K1a -> K1b hand-off).  sonics_scratch_bytes(n_units, max_window) is the size that runs
+ * n_units = n_active * sim_count in a single chunk; anything from sonics_scratch_bytes(32, max_window)
+ * up works (more chunks, two launches each). */
+size_t sonics_scratch_bytes(int64_t n_units, int max_window);
 
 /* ---- K2/K3: per-genotype statistics on the cumulative lnL arrays ---------
  * Restates sonics.pyx:136-191 (+ :208-252 for the final verdict): grouping,
  * min_sim, top-2 groups by max lnL, 75th-percentile difference, one-sided
  * Mann-Whitney U of the best group against every other group with Bonferroni,
- * PASS predicate.  n_run = cumulative simulations per genotype (<= SONICS_STATS_MAX_REPS).
+ * PASS predicate.  n_run = cumulative simulations per genotype; up to SONICS_STATS_MAX_REPS the whole
+ * reduction runs on chip (one CTA per genotype), above it through CUB sorts and scans over dev_scratch.
  * final_round != 0 also fills the FILTER bits of a non-passing genotype.  dev_identity / dev_rsq
  * are only read in --monte_carlo mode (sonics.pyx:115-131) and may be NULL otherwise.
  * Verdicts are written to dev_verdict[g] (genotype index). */
 int sonics_evaluate(sonics_ctx *ctx, const SonicsParams *params, const void *dev_table, int n_gt,
                     const int32_t *dev_active, int n_active, int64_t n_run, int64_t out_stride, const double *dev_lnL,
                     const uint16_t *dev_group, const double *dev_identity, const float *dev_rsq, int final_round,
-                    SonicsVerdict *dev_verdict, void *stream);
+                    SonicsVerdict *dev_verdict, void *dev_scratch, size_t dev_scratch_bytes, void *stream);
+/* Scratch sonics_evaluate needs when n_run > SONICS_STATS_MAX_REPS (CUB sort / scan path, one genotype
+ * at a time); 0 below that, where dev_scratch may be NULL. */
+size_t sonics_stats_scratch_bytes(int64_t n_run, int max_alleles, int random_start);
 
 /* K4: replay simulation dev_verdict[g].best_sim of every listed genotype (same Philox stream, hence
  * the same PCR pool and lnL) with the sequencing readout switched on, and fill dev_verdict[g].identity
@@ -174,7 +184,7 @@ int sonics_evaluate(sonics_ctx *ctx, const SonicsParams *params, const void *dev
  * is negative (no_success) are skipped. */
 int sonics_replay_best(sonics_ctx *ctx, const SonicsParams *params, const void *dev_table, int n_gt,
                        const int32_t *dev_active, int n_active, uint64_t seed, SonicsVerdict *dev_verdict,
-                       void *stream);
+                       void *dev_scratch, size_t dev_scratch_bytes, void *stream);
 
 /* ---- the whole repeat-until-pass loop for a batch of genotypes ------------
  * Equivalent of mapping process_one_genotype() -> monte_carlo() over the list
@@ -198,7 +208,7 @@ int sonics_genotype_batch(sonics_ctx *ctx, const SonicsParams *params, int n_gt,
 /* sonics_debug_counters: while dev_counters (16 x u64 of caller-owned device memory, zeroed by the
  * caller) is non-NULL, sonics_simulate accumulates K1 control-flow statistics into it: [0] passes,
  * [1..7] lanes per state-machine mode summed over passes, [8] ADVANCE inner trips, [9] lanes entering
- * ADVANCE, [10] deferred-test executions, [11] lanes served by them, [12] warp work items. */
+ * ADVANCE, [10] deferred-test executions, [11] lanes served by them, [12] warps. */
 int sonics_debug_counters(sonics_ctx *ctx, uint64_t *dev_counters);
 int sonics_debug_philox(sonics_ctx *ctx, uint64_t seed, uint64_t sim, uint32_t uid, uint32_t stream_id, int n_blocks,
                         uint32_t *dev_out);

@@ -81,9 +81,12 @@ PROTOTYPES = {
     "sonics_table_build": (_I, [_P, ctypes.POINTER(SonicsParams), _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "sonics_table_max_window": (_I, [_P]),
     "sonics_simulate": (_I, [_P, ctypes.POINTER(SonicsParams), _P, _I, _P, _I, _I64, _I64, _U64, _I64, _I64, _P, _P,
-                             _P, _P, _P, _P]),
-    "sonics_evaluate": (_I, [_P, ctypes.POINTER(SonicsParams), _P, _I, _P, _I, _I64, _I64, _P, _P, _P, _P, _I, _P, _P]),
-    "sonics_replay_best": (_I, [_P, ctypes.POINTER(SonicsParams), _P, _I, _P, _I, _U64, _P, _P]),
+                             _P, _P, _P, _P, _SZ, _P]),
+    "sonics_scratch_bytes": (_SZ, [_I64, _I]),
+    "sonics_evaluate": (_I, [_P, ctypes.POINTER(SonicsParams), _P, _I, _P, _I, _I64, _I64, _P, _P, _P, _P, _I, _P, _P,
+                             _SZ, _P]),
+    "sonics_stats_scratch_bytes": (_SZ, [_I64, _I, _I]),
+    "sonics_replay_best": (_I, [_P, ctypes.POINTER(SonicsParams), _P, _I, _P, _I, _U64, _P, _P, _SZ, _P]),
     "sonics_genotype_work_bytes": (_SZ, [_I, _I, _I]),
     "sonics_genotype_batch": (_I, [_P, ctypes.POINTER(SonicsParams), _I, _P, _P, _P, _P, _P, _I, _U64, _P, _P, _SZ,
                                    _P]),

@@ -11,13 +11,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsonics_b200.so")
 SOURCES = ["sonics_b200.cu"]
-DEPS = ["sonics_b200.cu", "sim_kernel.cuh", "stats_kernel.cuh", "abi_stats.inl", "samplers.cuh", "rng.cuh", "lnl.cuh",
+DEPS = ["sonics_b200.cu", "sim_kernel.cuh", "stats_kernel.cuh", "stats_big.cuh", "abi_stats.inl", "samplers.cuh", "rng.cuh", "lnl.cuh",
         os.path.join("..", "..", "include", "sonics_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC,-ffp-contract=off",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-Wno-deprecated-declarations",
     "-shared",
 ]
 

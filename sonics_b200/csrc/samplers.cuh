@@ -41,44 +41,45 @@ __device__ __forceinline__ float floor_small(float x) { return __fadd_rd(x, 1258
 // ---- building blocks -------------------------------------------------------------------------
 // The samplers are split into setup / one-trial / deferred-test pieces so that K1's per-lane state
 // machine can interleave them across lanes (one rejection trial or one chunk of inversion steps per
-// pass, the rare Stirling test batched over several lanes).  binomial() below composes the same
-// pieces in lockstep form and is what the exact-pmf tests exercise.
-
-struct InvState { // inversion: Binomial(n, p), p <= 0.5, n*p < 10
-    float u, px, a, s;
-    int x, cap;
+// pass, the rare Stirling test batched over several lanes).  binomial() / poisson() below compose
+// the same pieces in lockstep form and are what the exact-pmf tests exercise.
+//
+// A lane has at most one draw in flight, so the three samplers share one register block:
+//   BTRS      fn p npq a b vr alpha ci cf fm | fk = candidate, A = ln of the scaled uniform
+//   inversion a = (n+1) p/q, b = p/q         | fk = u (remaining uniform), A = px, ix = x, icap = cap
+//   PTRS      fn = lam (the reference's fp32 `hit`), a b vr, alpha = 1/alpha | ix = candidate
+struct DrawState {
+    float fn, p, npq, a, b, vr, alpha, ci, cf, fm, fk, A;
+    int ix, icap;
 };
 
-__device__ __forceinline__ void inv_setup(InvState &v, int n, float p)
+// ---- inversion: Binomial(n, p), p <= 0.5, n*p < 10 ----
+__device__ __forceinline__ void inv_setup(DrawState &v, int n, float p)
 {
     const float q = 1.0f - p;
-    v.s = __fdividef(p, q);
-    v.a = (float)(n + 1) * v.s;
-    v.px = __expf((float)n * log1pf(-p)); // q^n
-    v.cap = n < SONICS_RCP_TABLE - 1 ? n : SONICS_RCP_TABLE - 1; // P(X > 160 | np < 10) < 1e-130
-    v.x = 0;
-    v.u = 0.0f;
+    v.b = __fdividef(p, q);
+    v.a = (float)(n + 1) * v.b;
+    v.A = __expf((float)n * log1pf(-p)); // px = q^n
+    v.icap = n < SONICS_RCP_TABLE - 1 ? n : SONICS_RCP_TABLE - 1; // P(X > 160 | np < 10) < 1e-130
+    v.ix = 0;
+    v.fk = 0.0f;
 }
-__device__ __forceinline__ void inv_start(InvState &v, uint32_t bits) { v.u = u01_fine(bits); }
-// up to max_steps steps of the sequential search; true when the draw is finished (result v.x)
-__device__ __forceinline__ bool inv_run(InvState &v, const float *rcp_tab, int max_steps)
+__device__ __forceinline__ void inv_start(DrawState &v, uint32_t bits) { v.fk = u01_fine(bits); }
+// up to max_steps steps of the sequential search; true when the draw is finished (result v.ix)
+__device__ __forceinline__ bool inv_run(DrawState &v, const float *rcp_tab, int max_steps)
 {
     int k = 0;
-    while (v.u > v.px && v.x < v.cap && k < max_steps) {
-        ++v.x;
+    while (v.fk > v.A && v.ix < v.icap && k < max_steps) {
+        ++v.ix;
         ++k;
-        v.u -= v.px;
-        v.px *= fmaf(v.a, rcp_tab[v.x], -v.s);
+        v.fk -= v.A;
+        v.A *= fmaf(v.a, rcp_tab[v.ix], -v.b);
     }
-    return !(v.u > v.px && v.x < v.cap);
+    return !(v.fk > v.A && v.ix < v.icap);
 }
 
-struct BtrsState { // BTRS: Binomial(n, p), p <= 0.5, n*p >= 10
-    float fn, p, npq, a, b, vr, alpha, ci, cf, fm;
-    float fk, A; // candidate and ln of the scaled uniform, kept for the deferred test
-};
-
-__device__ __forceinline__ void btrs_setup(BtrsState &s, int n, float p)
+// ---- BTRS: Binomial(n, p), p <= 0.5, n*p >= 10 ----
+__device__ __forceinline__ void btrs_setup(DrawState &s, int n, float p)
 {
     s.fn = (float)n;
     s.p = p;
@@ -100,7 +101,7 @@ __device__ __forceinline__ void btrs_setup(BtrsState &s, int n, float p)
 
 // One rejection trial.  0 = rejected, 1 = accepted (result s.fk), 2 = undecided: s.fk / s.A hold the
 // candidate for btrs_full().
-__device__ __forceinline__ int btrs_trial(BtrsState &s, uint32_t bits_a, uint32_t bits_b)
+__device__ __forceinline__ int btrs_trial(DrawState &s, uint32_t bits_a, uint32_t bits_b)
 {
     const float u = u01_open(bits_a) - 0.5f;
     const float v = u01_open(bits_b);
@@ -131,7 +132,7 @@ __device__ __forceinline__ int btrs_trial(BtrsState &s, uint32_t bits_a, uint32_
 
 // The exact test for an undecided candidate: A <= ln f(k)/f(m), every term conditioned through
 // log1p so that each is O(|k-m|).
-__device__ __forceinline__ bool btrs_full(const BtrsState &s)
+__device__ __forceinline__ bool btrs_full(const DrawState &s)
 {
     const float q = 1.0f - s.p;
     const float r = __fdividef(s.p, q);
@@ -156,16 +157,15 @@ __device__ __forceinline__ int binomial(Rng &rng, int n, float p, uint32_t bits_
         return n;
     const bool flip = p > 0.5f;
     const float pp = flip ? 1.0f - p : p;
+    DrawState s;
     int k;
     if ((float)n * pp < 10.0f) {
-        InvState v;
-        inv_setup(v, n, pp);
-        inv_start(v, bits_a);
-        while (!inv_run(v, rcp_tab, 1 << 20))
+        inv_setup(s, n, pp);
+        inv_start(s, bits_a);
+        while (!inv_run(s, rcp_tab, 1 << 20))
             ;
-        k = v.x;
+        k = s.ix;
     } else {
-        BtrsState s;
         btrs_setup(s, n, pp);
         PairSource src(rng, bits_a, bits_b);
         while (true) {
@@ -180,67 +180,73 @@ __device__ __forceinline__ int binomial(Rng &rng, int n, float p, uint32_t bits_
 }
 
 // ---- Poisson ---------------------------------------------------------------------------------
-// lam arrives as the reference's fp32 `hit` widened to double.  Rare (one draw per non-zero bin per
-// reaction, at the capture cycle), so the acceptance test simply runs in fp64.
-struct PoisState {
-    double lam, loglam;
-    float a, b, invalpha, vr;
-    int k;
-};
+// lam is the reference's fp32 `hit` (sonics.pyx:419-420).  PTRS (Hoermann 1993) in the same
+// split-fp32 style as BTRS: the proposal keeps the integer part of lam exactly, and the acceptance
+// test uses  ln f(k) = k (log1p(y) - y) - ln(2 pi k)/2 - 1/(12k) + 1/(360 k^3),  y = (lam - k)/k,
+// whose terms are O((k - lam)^2 / k) instead of O(lam ln lam).
 
 // Poisson(lam) for 0 < lam < 10: sequential inversion, run to completion.
-__device__ __forceinline__ int poisson_small(double lam, uint32_t bits)
+__device__ __forceinline__ int poisson_small(float lam, uint32_t bits)
 {
-    float px = __expf(-(float)lam);
+    float px = __expf(-lam);
     float u = u01_fine(bits);
-    const float fl = (float)lam;
     int x = 0;
     while (u > px && x < 200) {
         ++x;
         u -= px;
-        px *= __fdividef(fl, (float)x);
+        px *= __fdividef(lam, (float)x);
     }
     return x;
 }
 
-__device__ __forceinline__ void pois_setup(PoisState &s, double lam) // lam >= 10: PTRS
+// PTRS state in DrawState: fn = lam, ci = floor(lam), cf = lam - ci + 0.43, a b vr, alpha = 1/alpha
+__device__ __forceinline__ void pois_setup(DrawState &s, float lam) // lam >= 10
 {
-    s.lam = lam;
-    const double slam = sqrt(lam);
-    s.loglam = log(lam);
-    s.b = (float)(0.931 + 2.53 * slam);
+    s.fn = lam;
+    const float slam = sqrtf(lam);
+    s.b = 0.931f + 2.53f * slam;
     s.a = -0.059f + 0.02483f * s.b;
-    s.invalpha = 1.1239f + __fdividef(1.1328f, s.b - 3.4f);
+    s.alpha = 1.1239f + __fdividef(1.1328f, s.b - 3.4f); // 1 / alpha
     s.vr = 0.9277f - __fdividef(3.6224f, s.b - 2.0f);
-    s.k = 0;
+    s.ci = floorf(lam);
+    s.cf = (lam - s.ci) + 0.43f;
+    s.ix = 0;
 }
 
-// One PTRS trial: true = accepted (result s.k)
-__device__ __forceinline__ bool pois_trial(PoisState &s, uint32_t bits_a, uint32_t bits_b)
+// One PTRS trial: true = accepted (result s.ix)
+__device__ __forceinline__ bool pois_trial(DrawState &s, uint32_t bits_a, uint32_t bits_b)
 {
     const float u = u01_open(bits_a) - 0.5f;
     const float v = u01_open(bits_b);
     const float us = 0.5f - fabsf(u);
-    const double kd = floor((double)(__fdividef(2.0f * s.a, us) + s.b) * (double)u + s.lam + 0.43);
-    s.k = (int)kd;
+    const float rus = __fdividef(1.0f, us);
+    const float fk = s.ci + floor_small(fmaf(fmaf(2.0f * s.a, rus, s.b), u, s.cf));
+    s.ix = (int)fk;
     if (us >= 0.07f && v <= s.vr)
         return true;
-    if (kd < 0.0 || (us < 0.013f && v > us))
+    if (fk < 0.0f || (us < 0.013f && v > us))
         return false;
-    const double lhs = (double)(__logf(v) + __logf(s.invalpha) - __logf(__fdividef(s.a, us * us) + s.b));
-    const double rhs = -s.lam + kd * s.loglam - lgamma(kd + 1.0);
+    const float lhs = __logf(v * s.alpha * __fdividef(1.0f, fmaf(s.a * rus, rus, s.b)));
+    float rhs;
+    if (fk >= 10.0f) {
+        const float rk = __fdividef(1.0f, fk);
+        const float y = (s.fn - fk) * rk;
+        rhs = fk * (log1pf(y) - y) - 0.5f * __logf(6.2831853f * fk) - rk * (0.083333333f - 0.0027777778f * rk * rk);
+    } else {
+        rhs = -s.fn + fk * __logf(s.fn) - lgammaf(fk + 1.0f);
+    }
     return lhs <= rhs;
 }
 
 // Poisson(lam), lockstep form.
-__device__ __forceinline__ int poisson(Rng &rng, double lam)
+__device__ __forceinline__ int poisson(Rng &rng, float lam)
 {
-    if (!(lam > 0.0))
+    if (!(lam > 0.0f))
         return 0;
     const uint4 r0 = rng.block4();
-    if (lam < 10.0)
+    if (lam < 10.0f)
         return poisson_small(lam, r0.x);
-    PoisState s;
+    DrawState s;
     pois_setup(s, lam);
     PairSource src(rng, r0.x, r0.y);
     src.sa = r0.z;
@@ -248,7 +254,7 @@ __device__ __forceinline__ int poisson(Rng &rng, double lam)
     src.spare = 1;
     while (!pois_trial(s, src.a, src.b))
         src.advance();
-    return s.k;
+    return s.ix;
 }
 
 } // namespace sonics

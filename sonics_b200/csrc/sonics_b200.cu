@@ -15,6 +15,7 @@
 #include "../../include/sonics_b200.h"
 #include "sim_kernel.cuh"
 #include "stats_kernel.cuh"
+#include "stats_big.cuh"
 
 using namespace sonics;
 
@@ -41,6 +42,7 @@ static int fail(int code, const char *fmt, ...)
 struct TableInfo {
     int n_gt, n_alleles, max_W, max_A;
     size_t off_allele, off_reads, off_fl;
+    std::vector<GtHeader> hdr; // host copy of the headers (the large-n statistics path needs A / first_idx)
 };
 
 struct sonics_ctx {
@@ -255,6 +257,7 @@ int sonics_table_build(sonics_ctx *ctx, const SonicsParams *params, int n_gt, co
     }
     ti.max_W = max_W;
     ti.max_A = max_A;
+    ti.hdr.assign(hdr, hdr + n_gt);
     CUDA_OK(cudaSetDevice(ctx->device));
     cudaStream_t s = (cudaStream_t)stream;
     CUDA_OK(cudaMemcpyAsync(dev_table, host.data(), host.size(), cudaMemcpyHostToDevice, s));
@@ -288,34 +291,70 @@ static int find_table(sonics_ctx *ctx, const void *dev_table, int n_gt, TableInf
     return SONICS_OK;
 }
 
-static int launch_simulate(sonics_ctx *ctx, SimArgs &a, const TableInfo &ti, bool readout, int64_t wpg, void *stream)
+// Scratch layout: [counters: 256 B][pool: ceil(units / 32) * Wcap * 32 int32]
+static size_t scratch_bytes_for(int64_t n_units, int Wcap)
 {
+    const int64_t tiles = (n_units + 31) / 32;
+    return 256 + (size_t)tiles * Wcap * 32 * 4;
+}
+
+// Runs units [0, total_units) of `a` (unit -> (slot, jrel) as documented at SimArgs) in chunks that
+// fit the caller's scratch: per chunk one persistent k_pcr launch and one k_lnl launch.
+static int launch_simulate(sonics_ctx *ctx, SimArgs &a, const TableInfo &ti, bool readout, int64_t total_units,
+                           void *dev_scratch, size_t scratch_bytes, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
     a.Wcap = ti.max_W;
-    a.warps_per_gt = (int32_t)wpg;
+    a.dbg = ctx->dbg;
+    if (!dev_scratch || scratch_bytes < scratch_bytes_for(32, a.Wcap))
+        return fail(SONICS_ERR_SPACE, "simulation scratch of %zu bytes is below the minimum %zu", scratch_bytes,
+                    scratch_bytes_for(32, a.Wcap));
+    const int64_t cap_units = std::min<int64_t>(((int64_t)(scratch_bytes - 256) / ((int64_t)a.Wcap * 128)) * 32,
+                                                 (int64_t)1 << 30);
+    a.counter = (unsigned int *)dev_scratch;
+    a.pool = (int32_t *)((unsigned char *)dev_scratch + 256);
     const size_t per_warp = warp_smem_bytes(a.Wcap);
     int wpb = (int)std::min<size_t>(4, (200 * 1024) / per_warp);
     if (wpb < 1)
         return fail(SONICS_ERR_RANGE, "window of %d bins does not fit shared memory", a.Wcap);
     const size_t smem = SONICS_RCP_TABLE * 4 + per_warp * wpb;
-    auto kern = readout ? k_simulate<true> : k_simulate<false>;
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaFuncSetAttribute(k_pcr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpb * 32, smem));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pcr, wpb * 32, smem));
     if (occ < 1)
         occ = 1;
-    const int64_t n_items = (int64_t)a.n_active * wpg;
-    const int64_t want = (n_items + wpb - 1) / wpb;
-    const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * occ);
-    kern<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(a);
-    ctx->launches++;
-    CUDA_OK(cudaGetLastError());
+    auto lnl = readout ? k_lnl<true> : k_lnl<false>;
+    for (int64_t u0 = 0; u0 < total_units; u0 += cap_units) {
+        const int64_t nu = std::min<int64_t>(cap_units, total_units - u0);
+        a.unit_base = u0;
+        a.n_units = (int32_t)nu;
+        CUDA_OK(cudaMemsetAsync(a.counter, 0, 256, s));
+        // persistent lanes: no more blocks than there are lanes' worth of work
+        const int64_t want = (nu + wpb * 32 - 1) / (wpb * 32);
+        const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * occ);
+        k_pcr<<<grid, wpb * 32, smem, s>>>(a);
+        ctx->launches++;
+        CUDA_OK(cudaGetLastError());
+        const int lgrid = (int)std::min<int64_t>((nu + 127) / 128, (int64_t)ctx->sm_count * 16);
+        lnl<<<lgrid, 128, 0, s>>>(a);
+        ctx->launches++;
+        CUDA_OK(cudaGetLastError());
+    }
     return SONICS_OK;
+}
+
+size_t sonics_scratch_bytes(int64_t n_units, int max_window)
+{
+    if (n_units <= 0 || max_window <= 0)
+        return 0;
+    return scratch_bytes_for(n_units, max_window);
 }
 
 int sonics_simulate(sonics_ctx *ctx, const SonicsParams *params, const void *dev_table, int n_gt,
                     const int32_t *dev_active, int n_active, int64_t sim_begin, int64_t sim_count, uint64_t seed,
                     int64_t out_stride, int64_t out_offset, double *dev_lnL, uint16_t *dev_group,
-                    double *dev_identity, float *dev_rsq, double *dev_simpar, void *stream)
+                    double *dev_identity, float *dev_rsq, double *dev_simpar, void *dev_scratch,
+                    size_t dev_scratch_bytes, void *stream)
 {
     if (!ctx || !dev_table || !dev_lnL || !dev_group)
         return fail(SONICS_ERR_ARG, "sonics_simulate: NULL argument");
@@ -323,6 +362,8 @@ int sonics_simulate(sonics_ctx *ctx, const SonicsParams *params, const void *dev
         return rc;
     if (sim_count <= 0 || sim_begin < 0)
         return fail(SONICS_ERR_ARG, "sonics_simulate: bad simulation range");
+    if (sim_count > 2147483647LL)
+        return fail(SONICS_ERR_RANGE, "sonics_simulate: sim_count too large");
     if (out_offset < 0 || out_stride < out_offset + sim_count)
         return fail(SONICS_ERR_SPACE, "sonics_simulate: out_stride %lld < out_offset + sim_count",
                     (long long)out_stride);
@@ -339,12 +380,8 @@ int sonics_simulate(sonics_ctx *ctx, const SonicsParams *params, const void *dev
     a.t = tv;
     a.p = dev_params(params);
     a.active = dev_active;
-    a.n_active = n_active;
-    const int64_t wpg = (sim_count + 31) / 32;
-    if (wpg > 2147483647LL)
-        return fail(SONICS_ERR_RANGE, "sonics_simulate: sim_count too large");
+    a.sims_per_gt = (int32_t)sim_count;
     a.sim_begin = sim_begin;
-    a.sim_count = sim_count;
     a.seed = seed;
     a.out_stride = out_stride;
     a.out_offset = out_offset;
@@ -354,9 +391,8 @@ int sonics_simulate(sonics_ctx *ctx, const SonicsParams *params, const void *dev
     a.rsq = dev_rsq;
     a.simpar = dev_simpar;
     a.replay = nullptr;
-    a.dbg = ctx->dbg;
     const bool readout = dev_identity != nullptr || dev_rsq != nullptr;
-    return launch_simulate(ctx, a, ti, readout, wpg, stream);
+    return launch_simulate(ctx, a, ti, readout, (int64_t)n_active * sim_count, dev_scratch, dev_scratch_bytes, stream);
 }
 
 int sonics_debug_counters(sonics_ctx *ctx, uint64_t *dev_counters)

@@ -200,13 +200,29 @@ class Engine:
         act_ptr, n_act = None, table.n_gt
         if active is not None:
             act_ptr, n_act = active.data_ptr(), int(active.numel())
+        scratch = self._scratch(n_act * int(sim_count), table.max_window)
         check(self.lib.sonics_simulate(
             self.ctx, ctypes.byref(params), table.buf.data_ptr(), table.n_gt, act_ptr, n_act, int(sim_begin),
             int(sim_count), int(seed) & 0xFFFFFFFFFFFFFFFF, int(stride), int(out_offset), out["lnL"].data_ptr(),
             out["group"].data_ptr(), out["identity"].data_ptr() if "identity" in out else None,
             out["rsq"].data_ptr() if "rsq" in out else None, out["simpar"].data_ptr() if "simpar" in out else None,
-            self._stream()))
+            scratch.data_ptr(), scratch.numel(), self._stream()))
         return out
+
+    SCRATCH_CAP = 2 << 30  # bytes; larger jobs run in chunks
+
+    def _scratch(self, n_units, max_window):
+        need = min(int(self.lib.sonics_scratch_bytes(int(n_units), int(max_window))), self.SCRATCH_CAP)
+        need = max(need, int(self.lib.sonics_scratch_bytes(32, int(max_window))))
+        return self._scratch_bytes(need)
+
+    def _scratch_bytes(self, need):
+        s = getattr(self, "_scratch_buf", None)
+        if s is None or s.numel() < need:
+            self._scratch_buf = None
+            s = self.torch.empty(need, dtype=self.torch.uint8, device=self.device)
+            self._scratch_buf = s
+        return s
 
     # -- K2/K3 ------------------------------------------------------------------
     def evaluate(self, params, table, out, n_run, final_round=True, active=None, verdict=None):
@@ -220,18 +236,25 @@ class Engine:
         act_ptr, n_act = None, table.n_gt
         if active is not None:
             act_ptr, n_act = active.data_ptr(), int(active.numel())
+        max_a = int(np.max(np.diff(table.allele_off)))
+        sbytes = int(self.lib.sonics_stats_scratch_bytes(int(n_run), max_a, int(params.random_start)))
+        sptr, snum = None, 0
+        if sbytes:
+            sc = self._scratch_bytes(sbytes)
+            sptr, snum = sc.data_ptr(), sc.numel()
         check(self.lib.sonics_evaluate(
             self.ctx, ctypes.byref(params), table.buf.data_ptr(), table.n_gt, act_ptr, n_act, int(n_run),
             int(out["lnL"].shape[1]), out["lnL"].data_ptr(), out["group"].data_ptr(),
             out["identity"].data_ptr() if "identity" in out else None,
             out["rsq"].data_ptr() if "rsq" in out else None, int(bool(final_round)), verdict.data_ptr(),
-            self._stream()))
+            sptr, snum, self._stream()))
         return verdict
 
     def replay_best(self, params, table, seed, verdict):
+        scratch = self._scratch(table.n_gt, table.max_window)
         check(self.lib.sonics_replay_best(self.ctx, ctypes.byref(params), table.buf.data_ptr(), table.n_gt, None,
                                           table.n_gt, int(seed) & 0xFFFFFFFFFFFFFFFF, verdict.data_ptr(),
-                                          self._stream()))
+                                          scratch.data_ptr(), scratch.numel(), self._stream()))
         return verdict
 
     def verdicts_to_host(self, verdict):

@@ -227,3 +227,74 @@ def test_outcome_distribution_matches_oracle():
     top_gpu = np.mean((v["allele_lo"] == 9) & (v["allele_hi"] == 11))
     top_orc = np.mean([i["genotype"] == "9/11" for i in infos])
     assert abs(top_gpu - top_orc) < tol
+
+
+def test_large_n_statistics_path_matches_oracle():
+    """n_run > 8192 goes through the CUB sort / scan path: same numbers as the numpy oracle."""
+    e = engine()
+    for gt, kw in ((CFG2, {}), (CFG1, {"random": True}), ("9|60;10|40;11|30;12|8", {"add_ratios": "0.5;0.9"})):
+        params = eng.make_params(**kw)
+        reads = orc.parse_reads(gt)
+        table = e.build_table_from_arrays(params, [reads, reads], [0.0, 0.0], uid=[5, 6])
+        n = 20000
+        out = e.simulate(params, table, n, seed=17)
+        v = e.verdicts_to_host(e.evaluate(params, table, out, n, final_round=True))
+        for g in range(2):
+            lnL = out["lnL"][g].cpu().numpy()
+            grp = out["group"][g].cpu().numpy().view(np.uint16)
+            labels = np.array([table.group_label(g, int(x)) for x in grp])
+            ev = stats.evaluate(lnL, labels, 25)
+            assert v[g]["run_reps"] == n and v[g]["min_sim"] == ev["min_sim"] and v[g]["n_groups"] == len(ev["groups"])
+            assert ev["evaluated"]
+            assert "%d/%d" % (v[g]["allele_lo"], v[g]["allele_hi"]) == ev["best"]
+            assert v[g]["best_lnL_ratio"] == ev["best_ratio"]
+            if not kw.get("add_ratios"):
+                assert v[g]["percentile_lnL_ratio"] == ev["pct_ratio"]
+            else:
+                sb, ss = ev["sorted_best"], ev["sorted_second"]
+                for i, q in enumerate((0.5, 0.9)):
+                    assert v[g]["add_ratio"][i] == stats.quantile_linear(sb, q) - stats.quantile_linear(ss, q)
+                assert v[g]["percentile_lnL_ratio"] == v[g]["add_ratio"][1]
+            hp = ev["high_pval"]
+            got = v[g]["high_pval"]
+            if v[g]["p_clamped"]:
+                assert hp >= 1
+            else:
+                assert abs(got - hp) <= 1e-10 * abs(hp) + 1e-300, (got, hp)
+            m = labels == ev["best"]
+            assert lnL[v[g]["best_sim"]] == lnL[m].max() == v[g]["lnL"]
+        # the on-chip path on the first 8000 simulations agrees with the oracle the same way (cross-check of both paths)
+        v2 = e.verdicts_to_host(e.evaluate(params, table, out, 8000, final_round=True))
+        lnL = out["lnL"][0, :8000].cpu().numpy()
+        labels = np.array([table.group_label(0, int(x)) for x in out["group"][0, :8000].cpu().numpy().view(np.uint16)])
+        ev = stats.evaluate(lnL, labels, 25)
+        assert v2[0]["best_lnL_ratio"] == ev["best_ratio"] and v2[0]["min_sim"] == ev["min_sim"]
+
+
+def test_large_n_monte_carlo_mode_cfg3():
+    """BASELINE config 3: --monte_carlo, 40 repeat-count bins, 30 cycles, -r 100000."""
+    from tests.util import CFG3
+    e = engine()
+    reads = orc.parse_reads(CFG3)
+    nc = orc.auto_noise_coef(reads)
+    params = eng.make_params(n_cycles=30, capture_cycle=16, monte_carlo=True)
+    off, al, rd = eng.to_csr([reads])
+    n = 100000
+    v = e.genotype_batch(params, off, al, rd, [nc], n, seed=3)[0]
+    assert v["run_reps"] == n and v["allele_lo"] >= 10 and v["allele_hi"] <= 49
+    table = e.build_table(params, off, al, rd, [nc])
+    out = e.simulate(params, table, n, seed=3, readout=True)
+    e.sync()
+    lnL = out["lnL"][0].cpu().numpy()
+    grp = out["group"][0].cpu().numpy().view(np.uint16)
+    ident = out["identity"][0].cpu().numpy()
+    rsq = out["rsq"][0].cpu().numpy().astype(np.float64)
+    bi = int(np.argmax(lnL))
+    assert v["best_sim"] == bi and v["lnL"] == lnL[bi] and v["identity"] == ident[bi] and v["r_squared"] == rsq[bi]
+    m = grp == grp[bi]
+    assert table.group_label(0, int(grp[bi])) == "%d/%d" % (v["allele_lo"], v["allele_hi"])
+    assert v["lnL_q75"] == stats.quantile_linear(np.sort(lnL[m]), 0.75)
+    assert v["identity_q75"] == stats.quantile_linear(np.sort(ident[m]), 0.75)
+    assert v["r_squared_q75"] == stats.quantile_linear(np.sort(rsq[m]), 0.75)
+    row = drop_in.format_row(v, {"monte_carlo": True}).split("\t")
+    assert len(row) == 8 and row[7] == str(n)

@@ -21,9 +21,9 @@ e.simulate(p, t, n, seed=1)
 e.sync()
 check(e.lib.sonics_debug_counters(e.ctx, None))
 c = cnt.cpu().numpy().astype(float)
-items = c[12]
-names = ["ADV", "BTRS", "INV0", "INV", "FULL", "POIS", "DONE"]
-print("warp items %d, passes/item %.1f" % (items, c[0] / items))
+warps = c[12]
+names = ["ADV", "BTRS", "INV0", "BOUND", "FULL", "POIS", "EXIT"]
+print("warps %d, passes/warp %.1f, passes per simulation-lane %.1f" % (warps, c[0] / warps, c[0] * 32 / n))
 for i, nm in enumerate(names):
     print("  lanes in %-5s per pass: %.2f" % (nm, c[1 + i] / c[0]))
 print("ADVANCE: lanes entering per pass %.2f, inner trips per pass %.2f" % (c[9] / c[0], c[8] / c[0]))
