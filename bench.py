@@ -192,6 +192,40 @@ def load_inst_per_reaction():
     return None
 
 
+def genotyping_throughput(e, eng, drop_in, n_loci=10000, n_samples=8):
+    """Second half of BASELINE.json's metric: loci genotyped/s (config 4: synthetic lobSTR-style VCF,
+    10k loci x 8 samples, default filters, the full repeat-until-pass loop).  Measured end to end
+    through sonics_genotype_batch with HOST buffers (CSR in, verdicts out), after one warm-up call."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import synth_vcf
+    from sonics_b200 import driver
+    loci = synth_vcf.make_genotypes(n_loci, n_samples, seed=20261019, cov=(50, 1000))
+    constants = {"one_allele_threshold": 45, "noise_threshold": 0.05}
+    work = []
+    for t in synth_vcf.genotype_strings(loci):
+        kind, payload = driver.prefilter(t, constants, {"monte_carlo": False})
+        if kind == "sim":
+            work.append(payload)
+    params = eng.make_params()
+    off, al, rd = eng.to_csr([w[0] for w in work])
+    noise = np.array([w[1] for w in work], dtype=np.float32)
+    e.genotype_batch(params, off[:1001], al[:off[1000]], rd[:off[1000]], noise[:1000], 1000, seed=1)  # warm-up
+    l0 = e.launches
+    t0 = time.perf_counter()
+    v = e.genotype_batch(params, off, al, rd, noise, 1000, seed=20261019)
+    dt = time.perf_counter() - t0
+    reps = v["run_reps"].astype(np.int64)
+    filt, cnt = np.unique(v["filter"], return_counts=True)
+    return {"value": len(work) / dt, "unit": "genotypes/s", "genotypes": len(work), "seconds": dt,
+            "reactions": int(reps.sum()), "reactions_per_s": float(reps.sum() / dt),
+            "repeats_hist": {str(k): int((reps == k).sum()) for k in (100, 500, 1000)},
+            "filter_hist": {drop_in.filter_string(int(f)) or "(none)": int(c) for f, c in zip(filt, cnt)},
+            "gpu_launches": int(e.launches - l0),
+            "workload": "cfg4: synthetic VCF %d loci x %d samples, coverage 50-1000, -r 1000, default filters; "
+                        "host CSR in -> verdicts out through sonics_genotype_batch" % (n_loci, n_samples)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -200,6 +234,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--sims", type=int, default=SIMS_PER_STEP, help="reactions per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-genotyping", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -330,6 +365,8 @@ def main():
             line["issue_roofline"] = {
                 "bound": "alu_issue", "achieved": ach, "peak": peak_issue, "unit": "warp-inst/s", "frac": ach / peak_issue,
                 "warp_inst_per_reaction": cnt["warp_inst_per_reaction"], "source": cnt.get("source")}
+        if world == 1 and not args.no_genotyping:
+            line["genotyping"] = genotyping_throughput(e, eng, drop_in)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))
