@@ -195,7 +195,7 @@ __device__ __forceinline__ size_t pool_index(int u, int Wcap, int bin)
     return ((size_t)(u >> 5) * Wcap + bin) * 32 + (u & 31);
 }
 
-enum { M_ADV = 0, M_BTRS = 1, M_INV0 = 2, M_BOUND = 3, M_FULL = 4, M_POIS = 5, M_EXIT = 6 };
+enum { M_ADV = 0, M_BTRS = 1, M_INV0 = 2, M_BOUND = 3, M_FULL = 4, M_POIS = 5, M_EXIT = 6, M_INVRUN = 7 };
 enum { PC_NEWSIM = 0, PC_RESULT = 1, PC_CAPRESULT = 2, PC_SCAN = 3 };
 // deferral thresholds: a minority phase runs when this many lanes wait for it (or nothing else can progress)
 #ifndef SONICS_THR_BOUND
@@ -402,39 +402,20 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
             int req = 0; // 1: binomial(dn, dp)   2: poisson(lam)
             float dp = 0.0f, lam = 0.0f;
             // ---- (1) consume the finished draw ----
+            // Written with selects instead of a branch per stage: the lanes of a pass are spread over
+            // the three stages, and a 3-way branch would run each third separately.
             if (pc == PC_RESULT) {
-                bool bin_done = false;
-                int down = 0;
-                if (stage == 0) {
-                    amp = x;
-                    if (n_stage == 1 || amp == 0) { // below the floor (:477-479), or nothing amplified
-                        cur += amp;
-                        bin_done = true;
-                    } else {
-                        stage = 1;
-                        dn = amp;
-                        dp = p_slip;
-                        req = 1;
-                    }
-                } else if (stage == 1) {
-                    slip = x;
-                    if (slip == 0) {
-                        cur += amp;
-                        bin_done = true;
-                    } else {
-                        stage = 2;
-                        dn = slip;
-                        dp = p_upn;
-                        req = 1;
-                    }
-                } else {
-                    down = slip - x; // mol_down = mol_slip - mol_up
-                    cur += amp - slip;
-                    if (down > 0)
-                        carry = x; // sic: up-stutter only lands when mol_down > 0 (:473-476)
-                    bin_done = true;
-                }
+                amp = stage == 0 ? x : amp;
+                slip = stage == 1 ? x : slip;
+                // the bin is finished after the third draw, after a draw that returned 0 (nothing
+                // amplified / nothing slipped), or after the single draw of a below-floor bin (:477-479)
+                const bool bin_done = stage == 2 || x == 0 || n_stage == 1;
                 if (bin_done) {
+                    const int slip_e = stage >= 1 ? slip : 0;
+                    const int up_e = stage == 2 ? x : 0;
+                    const int down = slip_e - up_e; // mol_down = mol_slip - mol_up
+                    cur += amp - slip_e;
+                    carry = down > 0 ? up_e : 0; // sic: up-stutter only lands when mol_down > 0 (:473-476)
                     if (b > 0)
                         hist[(b - 1) * 32] = prev + down;
                     if (down > 0 && b - 1 < live_lo)
@@ -446,6 +427,11 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
                     E_up = fmaf(E_up + 1.0f, e1_up, E_up); // expm1((al+1) L) from expm1(al L)
                     E_dn = fmaf(E_dn + 1.0f, e1_dn, E_dn);
                     pc = PC_SCAN;
+                } else {
+                    ++stage;
+                    dn = x;
+                    dp = stage == 1 ? p_slip : p_upn;
+                    req = 1;
                 }
             } else if (pc == PC_CAPRESULT) {
                 hist[cap_b * 32] = x < cap_v ? x : cap_v; // ct_up = min(poisson(hit), ct) (:421)
@@ -552,36 +538,35 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
             ++c_pass;
 #pragma unroll
             for (int mm = 0; mm < 7; ++mm)
-                c_mode[mm] += __popc(__ballot_sync(SONICS_FULL, mode == mm));
+                c_mode[mm] += __popc(__ballot_sync(SONICS_FULL, mode == mm || (mm == M_INV0 && mode == M_INVRUN)));
         }
         const unsigned m_busy = __ballot_sync(SONICS_FULL, mode == M_ADV || mode == M_BTRS || mode == M_POIS);
 
-        // ================= INV (deferred): small-mean binomials by inversion, run to completion =================
+        // ================= INV (deferred) + one rejection step: shared random-word fetch =================
+        // Small-mean binomials are drawn by inversion when enough lanes wait for it (set-up, then
+        // bounded chunks of the sequential search: stragglers continue in the next INV run together
+        // with the newcomers).  Lanes in a rejection sampler run ONE trial per pass (an immediate
+        // retry would execute with ~1 lane).  Every lane that consumes randomness in this pass takes
+        // the next 128-bit block of ITS OWN simulation's stream -- the block counter advances only
+        // when the simulation consumes, never with the warp's pass count -- through one call site.
         {
-            const unsigned m_inv = __ballot_sync(SONICS_FULL, mode == M_INV0);
-            if (__popc(m_inv) >= SONICS_THR_INV || (m_inv != 0u && m_busy == 0u)) {
+            const unsigned m_inv = __ballot_sync(SONICS_FULL, mode == M_INV0 || mode == M_INVRUN);
+            const bool run_inv = __popc(m_inv) >= SONICS_THR_INV || (m_inv != 0u && m_busy == 0u);
+            uint4 words = make_uint4(0u, 0u, 0u, 0u);
+            if (mode == M_BTRS || mode == M_POIS || (run_inv && mode == M_INV0))
+                words = rng.block4();
+            if (run_inv && (mode == M_INV0 || mode == M_INVRUN)) {
                 if (mode == M_INV0) {
                     inv_setup(ds, dn, ds.p);
-                    const uint4 words = rng.block4();
                     inv_start(ds, words.x);
-                    while (!inv_run(ds, rcp_tab, 1 << 20))
-                        ;
+                    mode = M_INVRUN;
+                }
+                if (inv_run(ds, rcp_tab, 6)) {
                     x = flip ? dn - ds.ix : ds.ix;
                     mode = M_ADV;
                 }
-            }
-        }
-
-        // ================= one rejection step of the draw in flight =================
-        // The lane takes the next 128-bit block of ITS OWN simulation's stream (the block counter
-        // advances only when the simulation consumes, never with the warp's pass count).  Both pairs
-        // are used within the pass: the second feeds an immediate retry after an outright rejection.
-        if (mode == M_BTRS || mode == M_POIS) {
-            const uint4 words = rng.block4();
-            if (mode == M_BTRS) {
-                int r = btrs_trial(ds, words.x, words.y);
-                if (r == 0)
-                    r = btrs_trial(ds, words.z, words.w);
+            } else if (mode == M_BTRS) {
+                const int r = btrs_trial(ds, words.x, words.y);
                 if (r == 1) {
                     const int k = (int)ds.fk;
                     x = flip ? dn - k : k;
@@ -589,11 +574,11 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
                 } else if (r == 2) {
                     mode = M_FULL;
                 }
-            } else {
+            } else if (mode == M_POIS) {
                 if (ds.fn < 10.0f) {
                     x = poisson_small(ds.fn, words.x);
                     mode = M_ADV;
-                } else if (pois_trial(ds, words.x, words.y) || pois_trial(ds, words.z, words.w)) {
+                } else if (pois_trial(ds, words.x, words.y)) {
                     x = ds.ix;
                     mode = M_ADV;
                 }
