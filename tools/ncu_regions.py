@@ -36,8 +36,7 @@ SIM = marks(os.path.join(CSRC, "sim_kernel.cuh"), [
     ("adv1_consume", "// ---- (1) consume the finished draw", "// ---- (2) walk to the next draw"),
     ("adv2_walk", "// ---- (2) walk to the next draw", "// ---- (3) classify the draw"),
     ("adv3_classify", "// ---- (3) classify the draw", "// ================= INV (deferred)"),
-    ("inv_phase", "// ================= INV (deferred)", "// ================= one rejection step"),
-    ("trial_phase", "// ================= one rejection step", "// ================= deferred Stirling test"),
+    ("inv_trial_phase", "// ================= INV (deferred)", "// ================= deferred Stirling test"),
     ("full_phase", "// ================= deferred Stirling test", "// K1b: one lane per simulation"),
 ])
 SMP = marks(os.path.join(CSRC, "samplers.cuh"), [
