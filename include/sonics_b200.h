@@ -214,6 +214,29 @@ int sonics_debug_philox(sonics_ctx *ctx, uint64_t seed, uint64_t sim, uint32_t u
                         uint32_t *dev_out);
 int sonics_debug_sample(sonics_ctx *ctx, int kind, int n, double p, int64_t count, uint64_t seed, int32_t *dev_out);
 
+/* ---- native host I/O (no GPU involved) ----------------------------------------------------------
+ * sonics_vcf_parse restates parse_vcf() (sonics:246-343), get_alleles() (sonics.pyx:17-31) and the
+ * pre-filters of process_one_genotype() (sonics:353-419: 0-/1-allele shortcuts, auto-noise rule) and
+ * returns the genotypes to simulate in the CSR form sonics_genotype_batch takes.  strict as --strict
+ * (the reference's two defects -- strict 0 IndexError, strict 2 column slip -- are not reproduced).
+ * sonics_vcf_count(what): 0 parsed genotypes, 1 genotypes to simulate, 2 CSR entries, 3 samples,
+ * 4 blocks, 5 warnings.  sonics_vcf_fill copies allele_off[n_sim+1], allele[], reads[], noise_coef[n_sim]
+ * and row_kind[n_parsed] (0 skipped, 1 no_simulations row, 2 simulated); any pointer may be NULL.
+ * sonics_rows_write writes the output file of run_sonics(): header (sonics:174-207) + one
+ * "sample\tblock\tref\t<row>" line (sonics:437) per genotype in input order, rows formatted as
+ * monte_carlo() does (sonics.pyx:122-134,208-269) with Python's str(float) number format; verdicts[i]
+ * belongs to the i-th simulated genotype.  vcf == NULL: string mode (one row: name, block, "."). */
+typedef struct sonics_vcf sonics_vcf;
+int sonics_vcf_parse(const char *path, int strict, int one_allele_threshold, double noise_threshold, int monte_carlo,
+                     uint64_t seed, sonics_vcf **out);
+void sonics_vcf_free(sonics_vcf *vcf);
+int64_t sonics_vcf_count(const sonics_vcf *vcf, int what);
+int sonics_vcf_fill(const sonics_vcf *vcf, int32_t *allele_off, int32_t *allele, int32_t *reads, float *noise_coef,
+                    int32_t *row_kind);
+const char *sonics_vcf_warning(const sonics_vcf *vcf, int64_t i);
+int sonics_rows_write(const char *path, const sonics_vcf *vcf, const SonicsVerdict *verdicts, int64_t n_verdicts,
+                      int monte_carlo, const char *add_ratios, const char *name, const char *block);
+
 /* Kernel launches issued by this ctx so far (bench.py's gpu_launches). */
 int64_t sonics_launch_count(sonics_ctx *ctx);
 

@@ -94,6 +94,12 @@ PROTOTYPES = {
     "sonics_debug_philox": (_I, [_P, _U64, _U64, ctypes.c_uint32, ctypes.c_uint32, _I, _P]),
     "sonics_debug_sample": (_I, [_P, _I, _I, ctypes.c_double, _I64, _U64, _P]),
     "sonics_launch_count": (_I64, [_P]),
+    "sonics_vcf_parse": (_I, [ctypes.c_char_p, _I, _I, ctypes.c_double, _I, _U64, ctypes.POINTER(_P)]),
+    "sonics_vcf_free": (None, [_P]),
+    "sonics_vcf_count": (_I64, [_P, _I]),
+    "sonics_vcf_fill": (_I, [_P, _P, _P, _P, _P, _P]),
+    "sonics_vcf_warning": (ctypes.c_char_p, [_P, _I64]),
+    "sonics_rows_write": (_I, [ctypes.c_char_p, _P, _P, _I64, _I, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]),
 }
 
 _lib = None

@@ -431,3 +431,4 @@ int sonics_debug_sample(sonics_ctx *ctx, int kind, int n, double p, int64_t coun
 } // extern "C"
 
 #include "abi_stats.inl"
+#include "host_io.inl"

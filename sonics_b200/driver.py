@@ -225,51 +225,120 @@ def run_batch(work, constants, ranges, options, seed, device=0, chunk=65536, uid
     return rows
 
 
+def run_batch_verdicts(allele_off, allele, reads, noise, constants, ranges, options, seed, device=0, chunk=65536,
+                       uid_offset=0):
+    """Verdict array for a CSR batch of genotypes (chunked); uid = global position keys the RNG."""
+    from . import engine as eng
+    e = sonics_mod.engine(device)
+    params = eng.params_from_dicts(constants, ranges, options)
+    n = len(noise)
+    parts = []
+    for c0 in range(0, n, chunk):
+        c1 = min(n, c0 + chunk)
+        off = allele_off[c0:c1 + 1] - allele_off[c0]
+        a0, a1 = allele_off[c0], allele_off[c1]
+        uids = np.arange(uid_offset + c0, uid_offset + c1, dtype=np.uint32)
+        parts.append(e.genotype_batch(params, off, allele[a0:a1], reads[a0:a1], noise[c0:c1], options["repetitions"],
+                                      seed, uid=uids))
+    return np.concatenate(parts) if parts else np.zeros(0, dtype=eng.VERDICT_DTYPE)
+
+
+def _csr_slice(allele_off, allele, reads, noise, lo, hi):
+    a0, a1 = allele_off[lo], allele_off[hi]
+    return allele_off[lo:hi + 1] - a0, allele[a0:a1], reads[a0:a1], noise[lo:hi]
+
+
+def _verdict_shard_worker(args):
+    off, al, rd, nz, constants, ranges, options, seed, device, chunk, lo = args
+    return run_batch_verdicts(off, al, rd, nz, constants, ranges, options, seed, device, chunk, uid_offset=lo)
+
+
 def run_sonics(feed_in, constants, ranges, options, seed=None, gpus=1, chunk=65536):
-    """run_sonics() of the reference (sonics:160-244) with the genotype loop batched on the GPU(s)."""
+    """run_sonics() of the reference (sonics:160-244) with the genotype loop batched on the GPU(s).
+
+    VCF ingest, the pre-filters of process_one_genotype() and the output writer run natively
+    (csrc/host_io.inl); parse_vcf() / prefilter() above are their Python mirrors (used with
+    --save_report, which needs the per-genotype path, and by the tests that pin the native code)."""
+    from . import hostio
     os.makedirs(options["out_path"], exist_ok=True)
     out_file_path = os.path.join(options["out_path"], options["file_name"])
     options["out_file_path"] = out_file_path
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), "little")
+    if options["save_report"]:
+        return _run_sonics_per_genotype(feed_in, constants, ranges, options, seed, out_file_path)
+    vcf = None
+    if options["vcf_mode"]:
+        vcf = hostio.Vcf(feed_in, options["strict"], constants["one_allele_threshold"], constants["noise_threshold"],
+                         options["monte_carlo"], seed)
+        if vcf.n_rows == 0:
+            raise Exception("No valid genotype after parsing VCF file.")
+        off, al, rd, nz = vcf.allele_off, vcf.allele, vcf.reads, vcf.noise_coef
+    else:
+        kind, payload = prefilter((options["name"], options["block"], ".", feed_in), constants, options)
+        if kind == "skip":
+            hostio.write_rows(out_file_path, np.zeros(0, dtype=hostio.VERDICT_DTYPE), None, options["monte_carlo"],
+                              options["add_ratios"], options["name"], options["block"])
+            return
+        if kind == "row":
+            with open(out_file_path, "w+") as f:
+                f.write("\t".join(HEADER_MC if options["monte_carlo"] else HEADER))
+                f.write("{}\t{}\t{}\t{}\n".format(options["name"], options["block"], ".", payload))
+            return
+        from . import engine as eng
+        off, al, rd = eng.to_csr([payload[0]])
+        nz = np.array([payload[1]], dtype=np.float32)
+    n = len(nz)
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            import torch
+            dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+        lo, hi = shard_bounds(n, world, rank)
+        local = int(os.environ.get("LOCAL_RANK", rank))
+        part = run_batch_verdicts(*_csr_slice(off, al, rd, nz, lo, hi), constants, ranges, options, seed, local, chunk, lo)
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(part, gathered, dst=0)  # ~170 B per genotype, host side; no collective on the data path
+        if rank != 0:
+            return
+        verdicts = np.concatenate(gathered)
+    elif gpus > 1:
+        import multiprocessing as mp
+        jobs = []
+        for r in range(gpus):
+            lo, hi = shard_bounds(n, gpus, r)
+            jobs.append(_csr_slice(off, al, rd, nz, lo, hi) + (constants, ranges, options, seed, r, chunk, lo))
+        with mp.get_context("spawn").Pool(gpus) as pool:
+            verdicts = np.concatenate(pool.map(_verdict_shard_worker, jobs))
+    else:
+        verdicts = run_batch_verdicts(off, al, rd, nz, constants, ranges, options, seed, 0, chunk)
+    hostio.write_rows(out_file_path, verdicts, vcf, options["monte_carlo"], options["add_ratios"], options["name"],
+                      options["block"])
+
+
+def _run_sonics_per_genotype(feed_in, constants, ranges, options, seed, out_file_path):
+    """--save_report: every simulation record is written (sonics.pyx:110-113, 201-206), one genotype at a time."""
     if options["vcf_mode"]:
         parsed = parse_vcf(feed_in, options["strict"])
         if not parsed:
             raise Exception("No valid genotype after parsing VCF file.")
     else:
         parsed = [(options["name"], options["block"], ".", feed_in)]
-    if seed is None:
-        seed = int.from_bytes(os.urandom(8), "little")
-    # host pre-filters, then one work list for the device
-    kinds = [prefilter(t, constants, options) for t in parsed]
-    sim_idx = [i for i, (k, _) in enumerate(kinds) if k == "sim"]
-    work = [kinds[i][1] for i in sim_idx]
-    if options["save_report"]:
-        # per-genotype path: every simulation record is written (sonics.pyx:110-113, 201-206)
-        rows = []
-        sonics_mod.seed(seed)
-        for i in sim_idx:
-            c = dict(constants, alleles=kinds[i][1][0], noise_coef=kinds[i][1][1])
-            o = dict(options, name=parsed[i][0], block=parsed[i][1])
-            rows.append(sonics_mod.monte_carlo(options["repetitions"], c, ranges, o))
-    elif world > 1:
-        rows = _run_sharded_torchrun(work, constants, ranges, options, seed, rank, world, chunk)
-    elif gpus > 1:
-        rows = _run_sharded_spawn(work, constants, ranges, options, seed, gpus, chunk)
-    else:
-        rows = run_batch(work, constants, ranges, options, seed, 0, chunk)
-    if rank != 0:
-        return
-    sim_rows = dict(zip(sim_idx, rows))
+    sonics_mod.seed(seed)
     with open(out_file_path, "w+") as out_file:
         out_file.write("\t".join(HEADER_MC if options["monte_carlo"] else HEADER))
-        for i, (name, block, ref, _) in enumerate(parsed):
-            kind, payload = kinds[i]
+        for t in parsed:
+            kind, payload = prefilter(t, constants, options)
             if kind == "skip":
                 continue
-            result = payload if kind == "row" else sim_rows[i]
-            logging.info(result)
-            out_file.write("{}\t{}\t{}\t{}\n".format(name, block, ref, result))
+            if kind == "sim":
+                c = dict(constants, alleles=payload[0], noise_coef=payload[1])
+                o = dict(options, name=t[0], block=t[1])
+                payload = sonics_mod.monte_carlo(options["repetitions"], c, ranges, o)
+            logging.info(payload)
+            out_file.write("{}\t{}\t{}\t{}\n".format(t[0], t[1], t[2], payload))
 
 
 def _run_sharded_torchrun(work, constants, ranges, options, seed, rank, world, chunk, batch_fn=None):
@@ -287,24 +356,6 @@ def _run_sharded_torchrun(work, constants, ranges, options, seed, rank, world, c
     if rank != 0:
         return []
     return [r for part in gathered for r in part]
-
-
-def _shard_worker(args):
-    work, constants, ranges, options, seed, device, chunk, lo = args
-    return run_batch(work, constants, ranges, options, seed, device, chunk, uid_offset=lo)
-
-
-def _run_sharded_spawn(work, constants, ranges, options, seed, gpus, chunk):
-    """--gpus N from a single command line: one worker process per GPU (spawn), rows gathered in order."""
-    import multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    jobs = []
-    for r in range(gpus):
-        lo, hi = shard_bounds(len(work), gpus, r)
-        jobs.append((work[lo:hi], constants, ranges, options, seed, r, chunk, lo))
-    with ctx.Pool(gpus) as pool:
-        parts = pool.map(_shard_worker, jobs)
-    return [r for part in parts for r in part]
 
 
 def main(argv=None):

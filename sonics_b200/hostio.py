@@ -1,0 +1,53 @@
+"""ctypes front-end of the native host I/O in libsonics_b200.so (csrc/host_io.inl):
+VCF ingest + pre-filters straight to CSR, and the output-file writer."""
+import ctypes
+import logging
+
+import numpy as np
+
+from . import _abi
+from ._abi import check
+from .engine import VERDICT_DTYPE
+
+
+class Vcf:
+    """Parsed lobSTR VCF: CSR of the genotypes to simulate + per-row kinds (0 skip, 1 no_simulations, 2 simulate)."""
+
+    def __init__(self, path, strict=1, one_allele_threshold=45, noise_threshold=0.05, monte_carlo=False, seed=0):
+        self.lib = _abi.load()
+        h = ctypes.c_void_p()
+        check(self.lib.sonics_vcf_parse(str(path).encode(), int(strict), int(one_allele_threshold),
+                                        float(noise_threshold), int(bool(monte_carlo)), int(seed) & (2**64 - 1),
+                                        ctypes.byref(h)))
+        self.handle = h
+        c = lambda w: int(self.lib.sonics_vcf_count(h, w))
+        self.n_rows, self.n_sim, n_entries, self.n_samples, self.n_blocks, n_warn = (c(i) for i in range(6))
+        self.allele_off = np.zeros(self.n_sim + 1, dtype=np.int32)
+        self.allele = np.zeros(n_entries, dtype=np.int32)
+        self.reads = np.zeros(n_entries, dtype=np.int32)
+        self.noise_coef = np.zeros(self.n_sim, dtype=np.float32)
+        self.row_kind = np.zeros(self.n_rows, dtype=np.int32)
+        check(self.lib.sonics_vcf_fill(h, self.allele_off.ctypes.data, self.allele.ctypes.data, self.reads.ctypes.data,
+                                       self.noise_coef.ctypes.data, self.row_kind.ctypes.data))
+        self.warnings = [self.lib.sonics_vcf_warning(h, i).decode("utf-8", "replace") for i in range(min(n_warn, 1000))]
+        for w in self.warnings[:20]:
+            logging.warning(w)
+
+    def close(self):
+        if self.handle:
+            self.lib.sonics_vcf_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def write_rows(path, verdicts, vcf=None, monte_carlo=False, add_ratios="", name="sample", block="Block"):
+    """Header + rows of run_sonics() (sonics:174-207, :437); verdicts: structured array (VERDICT_DTYPE)."""
+    lib = _abi.load()
+    v = np.ascontiguousarray(verdicts, dtype=VERDICT_DTYPE)
+    check(lib.sonics_rows_write(str(path).encode(), vcf.handle if vcf is not None else None, v.ctypes.data, len(v),
+                                int(bool(monte_carlo)), add_ratios.encode(), name.encode(), block.encode()))

@@ -1,0 +1,126 @@
+"""CPU tests of the native host I/O (csrc/host_io.inl) against its Python mirrors: VCF ingest +
+pre-filters -> CSR, Python-compatible float formatting, and the output-file writer."""
+import os
+import random
+import struct
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+from sonics_b200 import driver, engine as eng, hostio, sonics as drop_in
+from tests.util import load
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+def _python_path(vcf_path, strict, monte_carlo=False):
+    constants = {"one_allele_threshold": 45, "noise_threshold": 0.05}
+    parsed = driver.parse_vcf(vcf_path, strict)
+    kinds = [driver.prefilter(t, constants, {"monte_carlo": monte_carlo}) for t in parsed]
+    work = [k[1] for k in kinds if k[0] == "sim"]
+    off, al, rd = eng.to_csr([w[0] for w in work])
+    return parsed, kinds, off, al, rd, np.array([w[1] for w in work], dtype=np.float32)
+
+
+@pytest.mark.parametrize("strict", [1, 2])
+def test_native_vcf_ingest_matches_python_mirror(strict):
+    import synth_vcf
+    texts = [load("vcf_parse.json")["vcf"]]
+    with tempfile.TemporaryDirectory() as d:
+        p0 = os.path.join(d, "golden.vcf")
+        open(p0, "w").write(texts[0])
+        p1 = os.path.join(d, "synth.vcf")
+        loci = synth_vcf.make_genotypes(40, 5, seed=9, cov=(20, 400), noisy=0.3)
+        synth_vcf.write_vcf(p1, loci, 5)
+        # sprinkle edge cases: single-allele samples above / below the threshold, empty support, duplicates
+        p2 = os.path.join(d, "edge.vcf")
+        open(p2, "w").write(
+            "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ta\tb\tc\td\n"
+            "L1\t1\t.\tN\t.\t.\t.\tXREF=3;END=9;MOTIF=AC;REF=12;\tGT:ALLREADS\t0/0:0|46\t0/0:0|45\t0/0:0|0;2|0\t0/0:-2|5;0|9;-2|7\n"
+            "L2\t2\t.\tN\t.\t.\t.\tMOTIF=GATA;REF=7.25;X=1\tGT:ALLREADS:DP\t0/0:-4|10;0|200;4|8:9\t0/0:-40|3;0|5\t.\t0/0:1|4;0|50;4|60\n")
+        for path in (p0, p1, p2):
+            parsed, kinds, off, al, rd, nz = _python_path(path, strict)
+            v = hostio.Vcf(path, strict)
+            if strict == 1:  # with strict 2 the mirror drops excluded samples before they become rows
+                assert v.n_rows == len(parsed)
+                assert list(v.row_kind) == [{"skip": 0, "row": 1, "sim": 2}[k[0]] for k in kinds]
+            assert (v.allele_off == off).all() and (v.allele == al).all() and (v.reads == rd).all()
+            assert (v.noise_coef == nz).all()
+            v.close()
+
+
+def test_native_vcf_errors():
+    with tempfile.NamedTemporaryFile("w", suffix=".vcf", delete=False) as f:
+        f.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ts1\nb\t1\t.\tN\t.\t.\t.\tMOTIF=AC;\tGT:ALLREADS\t0/0:0|5\n")
+    try:
+        with pytest.raises(Exception, match="expecting REF"):
+            hostio.Vcf(f.name)
+    finally:
+        os.unlink(f.name)
+    with pytest.raises(Exception, match="cannot open"):
+        hostio.Vcf("/nonexistent/file.vcf")
+
+
+def _random_doubles(n, seed=1):
+    rnd = random.Random(seed)
+    out = [0.0, -0.0, 1.0, -1.0, 0.1, 1e-4, 9.999e-5, 1e-5, 1e15, 1e16, 9.999999999999998e15, 123456789012345680.0,
+           0.9033816425120773, -7.919938269071281, 6.471387605701286e-10, 65.68490269267932, -2.000000054512845e+16,
+           5e-324, 1.7976931348623157e308, 0.9586113691329956, 100.0, 2.5e-3]
+    while len(out) < n:
+        bits = rnd.getrandbits(64)
+        x = struct.unpack("<d", struct.pack("<Q", bits))[0]
+        if x == x and abs(x) != float("inf"):
+            out.append(x)
+        out.append(rnd.uniform(-500, 10) * 10 ** rnd.randint(-12, 3))
+    return out
+
+
+def test_rows_writer_matches_python_format(tmp_path):
+    vals = _random_doubles(4000)
+    n = len(vals) // 8
+    v = np.zeros(n, dtype=eng.VERDICT_DTYPE)
+    rs = np.random.RandomState(0)
+    v["allele_lo"] = rs.randint(1, 40, n)
+    v["allele_hi"] = v["allele_lo"] + rs.randint(0, 4, n)
+    v["filter"] = rs.choice([1, 2, 4, 8, 6, 10, 12, 14, 16, 0], n)
+    v["run_reps"] = rs.choice([100, 500, 1000], n)
+    v["p_clamped"] = rs.rand(n) < 0.1
+    for k, fld in enumerate(["identity", "r_squared", "lnL", "high_pval", "best_lnL_ratio", "percentile_lnL_ratio",
+                             "identity_q75", "r_squared_q75"]):
+        v[fld] = vals[k * n:(k + 1) * n]
+    v["lnL_q75"] = v["lnL"] - 1.5
+    v["add_ratio"][:, 0] = v["best_lnL_ratio"] * 0.5
+    v["add_ratio"][:, 1] = v["percentile_lnL_ratio"] * 3
+    for mc, add in ((False, ""), (False, "0.5;0.9"), (True, "")):
+        path = tmp_path / "out.txt"
+        for i in range(0, n, 97):  # string mode writes one row: check a sample of verdicts
+            hostio.write_rows(path, v[i:i + 1], None, mc, add, "S", "B")
+            lines = open(path).read().split("\n")
+            assert lines[0] == "\t".join(driver.HEADER_MC if mc else driver.HEADER).rstrip("\n")
+            assert lines[1] == "S\tB\t.\t" + drop_in.format_row(v[i], {"monte_carlo": mc, "add_ratios": add})
+    # skipped genotype in string mode: header only
+    hostio.write_rows(tmp_path / "e.txt", v[:0], None, False, "")
+    assert open(tmp_path / "e.txt").read().count("\n") == 1
+
+
+def test_rows_writer_vcf_mode_order_and_no_simulations(tmp_path):
+    p = tmp_path / "in.vcf"
+    p.write_text("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ta\tb\tc\n"
+                 "L1\t1\t.\tN\t.\t.\t.\tMOTIF=AC;REF=12;\tGT:ALLREADS\t0/0:0|46\t0/0:0|45\t0/0:-2|5;0|9\n"
+                 "L2\t2\t.\tN\t.\t.\t.\tMOTIF=AC;REF=20;\tGT:ALLREADS\t0/0:-2|50;0|60\t0/0:0|0\t0/0:2|7;0|90\n")
+    vcf = hostio.Vcf(p)
+    assert list(vcf.row_kind) == [1, 0, 2, 2, 0, 2] and vcf.n_sim == 3
+    v = np.zeros(3, dtype=eng.VERDICT_DTYPE)
+    v["allele_lo"], v["allele_hi"], v["filter"], v["run_reps"] = [11, 19, 20], [12, 20, 21], [1, 16, 2], [100, 1000, 1000]
+    v["lnL"] = [-3.5, 0, -8.25]
+    out = tmp_path / "o.txt"
+    hostio.write_rows(out, v, vcf)
+    lines = open(out).read().strip().split("\n")[1:]
+    assert lines[0] == "a\tL1\t12\t12/12\t.\t.\t.\tno_simulations\t.\t.\t.\t0\t."
+    assert lines[1].startswith("c\tL1\t12\t11/12\t") and lines[2].startswith("a\tL2\t20\t./.\t.\t.\t.\tno_success")
+    assert lines[3].startswith("c\tL2\t20\t20/21\t") and len(lines) == 4
+    with pytest.raises(Exception, match="verdicts for more genotypes"):
+        hostio.write_rows(out, v[:2], vcf)
