@@ -217,11 +217,27 @@ def genotyping_throughput(e, eng, drop_in, n_loci=10000, n_samples=8):
     dt = time.perf_counter() - t0
     reps = v["run_reps"].astype(np.int64)
     filt, cnt = np.unique(v["filter"], return_counts=True)
+    # the same job file to file: VCF text -> native ingest + pre-filters -> GPU loop -> sonics_out.txt
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        vcf_path = os.path.join(d, "cfg4.vcf")
+        synth_vcf.write_vcf(vcf_path, loci, n_samples)
+        args = driver.build_parser().parse_args(["-m", vcf_path, "-o", d, "--seed", "20261019"])
+        c, r, o = driver.dicts_from_args(args)
+        import logging
+        logging.disable(logging.WARNING)
+        t1 = time.perf_counter()
+        driver.run_sonics(vcf_path, c, r, o, seed=20261019)
+        file_dt = time.perf_counter() - t1
+        logging.disable(logging.NOTSET)
+        n_lines = sum(1 for _ in open(os.path.join(d, "sonics_out.txt"))) - 1
     return {"value": len(work) / dt, "unit": "genotypes/s", "genotypes": len(work), "seconds": dt,
             "reactions": int(reps.sum()), "reactions_per_s": float(reps.sum() / dt),
             "repeats_hist": {str(k): int((reps == k).sum()) for k in (100, 500, 1000)},
             "filter_hist": {drop_in.filter_string(int(f)) or "(none)": int(c) for f, c in zip(filt, cnt)},
             "gpu_launches": int(e.launches - l0),
+            "file_to_file": {"value": n_lines / file_dt, "unit": "genotypes/s", "seconds": file_dt, "rows": n_lines,
+                             "what": "sonics -m cfg4.vcf: native VCF ingest + pre-filters, GPU loop, native row writer"},
             "workload": "cfg4: synthetic VCF %d loci x %d samples, coverage 50-1000, -r 1000, default filters; "
                         "host CSR in -> verdicts out through sonics_genotype_batch" % (n_loci, n_samples)}
 
