@@ -380,7 +380,11 @@ def main():
             line["roofline"]["traffic"] = cnt.get("dram_bytes_per_launch")
             line["issue_roofline"] = {
                 "bound": "alu_issue", "achieved": ach, "peak": peak_issue, "unit": "warp-inst/s", "frac": ach / peak_issue,
-                "warp_inst_per_reaction": cnt["warp_inst_per_reaction"], "source": cnt.get("source")}
+                "warp_inst_per_reaction": cnt["warp_inst_per_reaction"],
+                "lanes_active_of_32": cnt.get("avg_active_threads"),
+                "note": "frac counts issued warp-instructions (ncu count x live rate); the lanes doing useful work "
+                        "per instruction are lanes_active_of_32",
+                "source": cnt.get("source")}
         if world == 1 and not args.no_genotyping:
             line["genotyping"] = genotyping_throughput(e, eng, drop_in)
         if world == 1 and not args.no_cpu_baseline:
