@@ -213,18 +213,6 @@ def shard_bounds(n, world, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def run_batch(work, constants, ranges, options, seed, device=0, chunk=65536, uid_offset=0):
-    """Rows for a list of ('sim', (alleles, noise)) items, in order; uid = global position keys the RNG."""
-    rows = []
-    for c0 in range(0, len(work), chunk):
-        part = work[c0:c0 + chunk]
-        uids = np.arange(uid_offset + c0, uid_offset + c0 + len(part), dtype=np.uint32)
-        r, _ = sonics_mod.monte_carlo_batch([w[0] for w in part], [w[1] for w in part], options["repetitions"],
-                                            constants, ranges, options, seed_value=seed, device=device, uids=uids)
-        rows.extend(r)
-    return rows
-
-
 def run_batch_verdicts(allele_off, allele, reads, noise, constants, ranges, options, seed, device=0, chunk=65536,
                        uid_offset=0):
     """Verdict array for a CSR batch of genotypes (chunked); uid = global position keys the RNG."""
@@ -241,6 +229,23 @@ def run_batch_verdicts(allele_off, allele, reads, noise, constants, ranges, opti
         parts.append(e.genotype_batch(params, off, allele[a0:a1], reads[a0:a1], noise[c0:c1], options["repetitions"],
                                       seed, uid=uids))
     return np.concatenate(parts) if parts else np.zeros(0, dtype=eng.VERDICT_DTYPE)
+
+
+def sharded(n, compute_shard, world=None, rank=None):
+    """One process per GPU under torchrun: rank r computes compute_shard(lo, hi) for its contiguous shard of the
+    n work items; rank 0 receives the parts in rank order (host-side gather_object, ~170 B per genotype -- there is
+    no collective on the data path).  Returns the list of parts on rank 0 and None elsewhere."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else world
+    rank = int(os.environ.get("RANK", "0")) if rank is None else rank
+    if not dist.is_initialized():
+        import torch
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+    lo, hi = shard_bounds(n, world, rank)
+    part = compute_shard(lo, hi)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(part, gathered, dst=0)
+    return gathered
 
 
 def _csr_slice(allele_off, allele, reads, noise, lo, hi):
@@ -292,18 +297,12 @@ def run_sonics(feed_in, constants, ranges, options, seed=None, gpus=1, chunk=655
         nz = np.array([payload[1]], dtype=np.float32)
     n = len(nz)
     if world > 1:
-        import torch.distributed as dist
-        if not dist.is_initialized():
-            import torch
-            dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
-        lo, hi = shard_bounds(n, world, rank)
         local = int(os.environ.get("LOCAL_RANK", rank))
-        part = run_batch_verdicts(*_csr_slice(off, al, rd, nz, lo, hi), constants, ranges, options, seed, local, chunk, lo)
-        gathered = [None] * world if rank == 0 else None
-        dist.gather_object(part, gathered, dst=0)  # ~170 B per genotype, host side; no collective on the data path
+        parts = sharded(n, lambda lo, hi: run_batch_verdicts(*_csr_slice(off, al, rd, nz, lo, hi), constants, ranges,
+                                                             options, seed, local, chunk, lo), world, rank)
         if rank != 0:
             return
-        verdicts = np.concatenate(gathered)
+        verdicts = np.concatenate(parts)
     elif gpus > 1:
         import multiprocessing as mp
         jobs = []
@@ -339,23 +338,6 @@ def _run_sonics_per_genotype(feed_in, constants, ranges, options, seed, out_file
                 payload = sonics_mod.monte_carlo(options["repetitions"], c, ranges, o)
             logging.info(payload)
             out_file.write("{}\t{}\t{}\t{}\n".format(t[0], t[1], t[2], payload))
-
-
-def _run_sharded_torchrun(work, constants, ranges, options, seed, rank, world, chunk, batch_fn=None):
-    """One process per GPU under torchrun: contiguous shards, host-side gather to rank 0, no collective
-    on the data path (verdict rows are ~100 B per genotype)."""
-    import torch.distributed as dist
-    if not dist.is_initialized():
-        import torch
-        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
-    lo, hi = shard_bounds(len(work), world, rank)
-    local = int(os.environ.get("LOCAL_RANK", rank))
-    rows = (batch_fn or run_batch)(work[lo:hi], constants, ranges, options, seed, local, chunk, uid_offset=lo)
-    gathered = [None] * world if rank == 0 else None
-    dist.gather_object(rows, gathered, dst=0)
-    if rank != 0:
-        return []
-    return [r for part in gathered for r in part]
 
 
 def main(argv=None):

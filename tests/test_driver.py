@@ -116,21 +116,26 @@ def test_synthetic_vcf_roundtrip():
 WORKER = textwrap.dedent("""
     import os, sys
     sys.path.insert(0, %r)
+    import numpy as np
     import torch.distributed as dist
     from sonics_b200 import driver
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    work = [("g%%d" %% i, 0.0) for i in range(11)]
-    def fake_batch(part, constants, ranges, options, seed, device, chunk, uid_offset=0):
-        return ["%%s:uid%%d:rank%%d" %% (w[0], uid_offset + k, rank) for k, w in enumerate(part)]
-    rows = driver._run_sharded_torchrun(work, {}, (), {}, 1, rank, world, 4, batch_fn=fake_batch)
+    off = np.array([0, 2, 5, 7, 9, 12, 14, 16, 19, 21, 23, 25], dtype=np.int32)  # 11 genotypes, ragged
+    al = np.arange(25, dtype=np.int32); rd = al + 1; nz = np.linspace(0, 1, 11).astype(np.float32)
+    def shard(lo, hi):
+        o, a, r, z = driver._csr_slice(off, al, rd, nz, lo, hi)
+        assert o[0] == 0 and o[-1] == len(a) == len(r) and len(z) == hi - lo
+        return [(lo + k, int(a[o[k]]), rank) for k in range(hi - lo)]   # (global position = RNG uid, first allele, rank)
+    parts = driver.sharded(11, shard)
     if rank == 0:
-        assert [r.split(":")[0] for r in rows] == ["g%%d" %% i for i in range(11)], rows
-        assert [r.split(":")[1] for r in rows] == ["uid%%d" %% i for i in range(11)], rows
-        assert rows[0].endswith("rank0") and rows[-1].endswith("rank1")
+        rows = [x for p in parts for x in p]
+        assert [x[0] for x in rows] == list(range(11)), rows
+        assert [x[1] for x in rows] == [int(al[off[g]]) for g in range(11)], rows
+        assert rows[0][2] == 0 and rows[-1][2] == 1
         print("GATHER_OK")
     else:
-        assert rows == []
+        assert parts is None
     dist.destroy_process_group()
 """)
 
