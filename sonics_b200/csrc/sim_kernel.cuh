@@ -398,6 +398,7 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
         // ================= ADVANCE =================
         if (a.dbg)
             c_adv_lanes += __popc(__ballot_sync(SONICS_FULL, mode == M_ADV));
+        const unsigned m_adv = __ballot_sync(SONICS_FULL, mode == M_ADV);
         if (mode == M_ADV) {
             int req = 0; // 1: binomial(dn, dp)   2: poisson(lam)
             float dp = 0.0f, lam = 0.0f;
@@ -508,6 +509,9 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
                 }
             }
             // ---- (3) classify the draw ----
+#ifndef SONICS_NO_RECONVERGE
+            __syncwarp(m_adv); // lanes leave the walk loop at different trips: classify / set up together
+#endif
             if (req == 1) {
                 if (!(dp > 0.0f)) { // degenerate priors only: consumed on the next pass without a draw
                     x = 0;
