@@ -210,6 +210,22 @@ int sonics_genotype_batch(sonics_ctx *ctx, const SonicsParams *params, int n_gt,
  * [1..7] lanes per state-machine mode summed over passes, [8] ADVANCE inner trips, [9] lanes entering
  * ADVANCE, [10] deferred-test executions, [11] lanes served by them, [12] warps. */
 int sonics_debug_counters(sonics_ctx *ctx, uint64_t *dev_counters);
+/* sonics_debug_trace: while dev_trace is non-NULL, sonics_simulate runs the traced instantiation of K1a and
+ * records, per simulation (unit = genotype slot * sim_count + simulation, all units must fit one scratch
+ * chunk), every random draw the simulation requests, in request order, with its outcome:
+ *   kind 1: Binomial(n, p) -> x   (sonics.pyx:454,458,462,478; draws with n == 0 are never requested)
+ *   kind 2: Poisson(p) of a bin holding n molecules -> x, before the min(x, n) of sonics.pyx:421
+ * dev_trace is [units][trace_cap] entries, dev_trace_len[unit] the number requested.  The final pool of unit
+ * u stays in the caller's scratch: bin c at int32 index 64 + ((u / 32) * max_window + c) * 32 + u % 32.
+ * tests/test_gpu_trace.py replays the reference's loop on the recorded outcomes (scripted draws)
+ * and requires bit-identical pools.  Pass NULL to switch tracing off. */
+typedef struct {
+    int32_t kind;
+    int32_t n;
+    float p;
+    int32_t x;
+} SonicsTraceEntry;
+int sonics_debug_trace(sonics_ctx *ctx, SonicsTraceEntry *dev_trace, int32_t trace_cap, int32_t *dev_trace_len);
 int sonics_debug_philox(sonics_ctx *ctx, uint64_t seed, uint64_t sim, uint32_t uid, uint32_t stream_id, int n_blocks,
                         uint32_t *dev_out);
 int sonics_debug_sample(sonics_ctx *ctx, int kind, int n, double p, int64_t count, uint64_t seed, int32_t *dev_out);

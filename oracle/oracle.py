@@ -98,6 +98,16 @@ def lib():
         L.oracle_run.restype = ctypes.c_int
         L.oracle_run.argtypes = [ctypes.POINTER(OracleCfg), ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32,
                                  ctypes.c_int64, ctypes.c_void_p]
+        L.oracle_replay_script.restype = ctypes.c_int
+        L.oracle_replay_script.argtypes = [ctypes.POINTER(OracleCfg), ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64),
+                                           ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                           ctypes.POINTER(ctypes.c_int64)]
+        L.oracle_record_script.restype = ctypes.c_int
+        L.oracle_record_script.argtypes = [ctypes.POINTER(OracleCfg), ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32,
+                                           ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64),
+                                           ctypes.c_void_p, ctypes.c_void_p]
         L.oracle_one_repeat.restype = ctypes.c_int
         L.oracle_one_repeat.argtypes = [ctypes.c_void_p, ctypes.POINTER(OracleCfg), ctypes.c_void_p, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p]
@@ -154,6 +164,47 @@ def run(cfg, alleles, seed, n):
     if rc == -1:
         raise Exception("Less then two alleles as starting conditions! Aborting.")
     return out
+
+
+SCRIPT_DTYPE = np.dtype([("kind", "<i4"), ("n", "<i4"), ("p", "<f4"), ("x", "<i4")])  # oracle_script_entry
+
+
+def replay_script(cfg, alleles, params4, start_idx, script):
+    """One one_repeat() (no readout) of the reference's loop on recorded draw outcomes.
+
+    params4 = (down, up, capture, efficiency); start_idx = the randint() results of the start-allele choice
+    (indices into the non-zero input alleles); script = SCRIPT_DTYPE records in request order.  Returns
+    (rc, record, pool[int64, max_allele], used, max_rel_dp, max_abs_dlam, err_pos); rc 0 = the script was
+    consistent with every request the loop made (kind and n equal, outcomes in range)."""
+    alleles = np.ascontiguousarray(alleles, dtype=np.int64)
+    params4 = np.ascontiguousarray(params4, dtype=np.float64)
+    start_idx = np.ascontiguousarray(start_idx, dtype=np.int64)
+    script = np.ascontiguousarray(script, dtype=SCRIPT_DTYPE)
+    rec = np.zeros(1, dtype=RECORD_DTYPE)
+    pool = np.zeros(alleles.shape[0], dtype=np.int64)
+    used, err_pos = ctypes.c_int64(0), ctypes.c_int64(0)
+    dp, dlam = ctypes.c_double(0), ctypes.c_double(0)
+    rc = lib().oracle_replay_script(ctypes.byref(cfg), alleles.ctypes.data, int(alleles.shape[0]),
+                                    params4.ctypes.data, start_idx.ctypes.data, int(start_idx.shape[0]),
+                                    script.ctypes.data, int(script.shape[0]), rec.ctypes.data, pool.ctypes.data,
+                                    ctypes.byref(used), ctypes.byref(dp), ctypes.byref(dlam), ctypes.byref(err_pos))
+    return rc, rec[0], pool, used.value, dp.value, dlam.value, err_pos.value
+
+
+def record_script(cfg, alleles, seed, cap=1 << 16):
+    """One sampled one_repeat() (no readout) -> (record, pool, script of its draws in request order)."""
+    alleles = np.ascontiguousarray(alleles, dtype=np.int64)
+    script = np.zeros(cap, dtype=SCRIPT_DTYPE)
+    rec = np.zeros(1, dtype=RECORD_DTYPE)
+    pool = np.zeros(alleles.shape[0], dtype=np.int64)
+    n = ctypes.c_int64(0)
+    rc = lib().oracle_record_script(ctypes.byref(cfg), alleles.ctypes.data, int(alleles.shape[0]),
+                                    int(seed) & 0xFFFFFFFF, script.ctypes.data, cap, ctypes.byref(n), rec.ctypes.data,
+                                    pool.ctypes.data)
+    if rc == -1:
+        raise Exception("Less then two alleles as starting conditions! Aborting.")
+    assert n.value <= cap, "script capacity %d < %d draws" % (cap, n.value)
+    return rec[0], pool, script[:n.value]
 
 
 def run_parallel(cfg, alleles, seed, n, threads=None, chunk=2000):

@@ -91,6 +91,7 @@ PROTOTYPES = {
     "sonics_genotype_batch": (_I, [_P, ctypes.POINTER(SonicsParams), _I, _P, _P, _P, _P, _P, _I, _U64, _P, _P, _SZ,
                                    _P]),
     "sonics_debug_counters": (_I, [_P, _P]),
+    "sonics_debug_trace": (_I, [_P, _P, ctypes.c_int32, _P]),
     "sonics_debug_philox": (_I, [_P, _U64, _U64, ctypes.c_uint32, ctypes.c_uint32, _I, _P]),
     "sonics_debug_sample": (_I, [_P, _I, _I, ctypes.c_double, _I64, _U64, _P]),
     "sonics_launch_count": (_I64, [_P]),

@@ -106,6 +106,11 @@ struct SimArgs {
     unsigned int *counter;   // scratch: next unit to hand out
     SonicsVerdict *replay;   // replay mode (K4)
     unsigned long long *dbg; // optional diagnostics (sonics_debug_counters)
+    // optional draw trace (sonics_debug_trace; k_pcr<true> only): every draw a simulation requests, in
+    // request order, with its outcome (the tests replay the reference's loop on these outcomes)
+    SonicsTraceEntry *trace; // [unit][trace_cap]
+    int32_t *trace_len;      // [unit] entries requested (may exceed trace_cap: the excess is not stored)
+    int32_t trace_cap;
 };
 enum { K1_CNT_PASSES = 0, K1_CNT_MODE0 = 1 /* .. +6: lanes per mode summed over passes */, K1_CNT_ADV_TRIPS = 8,
        K1_CNT_ADV_LANES = 9, K1_CNT_FULL_RUNS = 10, K1_CNT_FULL_LANES = 11, K1_CNT_WARPS = 12 };
@@ -202,10 +207,13 @@ enum { PC_NEWSIM = 0, PC_RESULT = 1, PC_CAPRESULT = 2, PC_SCAN = 3 };
 #define SONICS_THR_BOUND 4
 #endif
 #ifndef SONICS_THR_INV
-#define SONICS_THR_INV 8
+#define SONICS_THR_INV 6
 #endif
 #ifndef SONICS_THR_FULL
 #define SONICS_THR_FULL 4
+#endif
+#ifndef SONICS_INV_CHUNK
+#define SONICS_INV_CHUNK 32 // sequential-search steps per pass (a bound, rarely reached: n*p < 10)
 #endif
 #ifndef SONICS_PCR_MIN_BLOCKS
 #define SONICS_PCR_MIN_BLOCKS 8
@@ -214,6 +222,7 @@ enum { PC_NEWSIM = 0, PC_RESULT = 1, PC_CAPRESULT = 2, PC_SCAN = 3 };
 // ---------------------------------------------------------------------------------------------
 // K1a
 // ---------------------------------------------------------------------------------------------
+template <bool TRACE>
 __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -248,6 +257,7 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
     int cap_b = 0, cap_hi = 0, cap_n = 1, cap_v = 0;
     float cap_set = 0.0f, floor_cap = 0.0f;
     DrawState ds;
+    int tr_n = 0; // TRACE: draws requested by the simulation in flight
 
     unsigned long long c_pass = 0, c_adv_trips = 0, c_adv_lanes = 0, c_full_runs = 0, c_full_lanes = 0;
     unsigned long long c_mode[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -270,6 +280,8 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
                         if (cycle > n_cycles) { // simulation finished: hand the pool to K1b
                             for (int c = 0; c < W; ++c)
                                 a.pool[pool_index(u, Wcap, c)] = hist[c * 32];
+                            if (TRACE)
+                                a.trace_len[u] = tr_n;
                             pc = PC_NEWSIM;
                         }
                     }
@@ -279,6 +291,7 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
                             mode = M_EXIT;
                         } else {
                             u = (int)t;
+                            tr_n = 0;
                             const int64_t gu = a.unit_base + u;
                             const int slot = (int)(gu / a.sims_per_gt);
                             const int jrel = (int)(gu - (int64_t)slot * a.sims_per_gt);
@@ -402,6 +415,8 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
         if (mode == M_ADV) {
             int req = 0; // 1: binomial(dn, dp)   2: poisson(lam)
             float dp = 0.0f, lam = 0.0f;
+            if (TRACE && (pc == PC_RESULT || pc == PC_CAPRESULT) && tr_n <= a.trace_cap)
+                a.trace[(size_t)u * a.trace_cap + tr_n - 1].x = x;
             // ---- (1) consume the finished draw ----
             // Written with selects instead of a branch per stage: the lanes of a pass are spread over
             // the three stages, and a 3-way branch would run each third separately.
@@ -512,6 +527,17 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
 #ifndef SONICS_NO_RECONVERGE
             __syncwarp(m_adv); // lanes leave the walk loop at different trips: classify / set up together
 #endif
+            if (TRACE && req != 0) {
+                if (tr_n < a.trace_cap) {
+                    SonicsTraceEntry e;
+                    e.kind = req;
+                    e.n = req == 1 ? dn : cap_v;
+                    e.p = req == 1 ? dp : lam;
+                    e.x = -1;
+                    a.trace[(size_t)u * a.trace_cap + tr_n] = e;
+                }
+                ++tr_n;
+            }
             if (req == 1) {
                 if (!(dp > 0.0f)) { // degenerate priors only: consumed on the next pass without a draw
                     x = 0;
@@ -565,7 +591,7 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
                     inv_start(ds, words.x);
                     mode = M_INVRUN;
                 }
-                if (inv_run(ds, rcp_tab, 6)) {
+                if (inv_run(ds, rcp_tab, SONICS_INV_CHUNK)) {
                     x = flip ? dn - ds.ix : ds.ix;
                     mode = M_ADV;
                 }

@@ -51,6 +51,9 @@ struct sonics_ctx {
     int64_t launches;
     int max_W_last;
     unsigned long long *dbg;
+    SonicsTraceEntry *trace; // sonics_debug_trace
+    int32_t *trace_len;
+    int32_t trace_cap;
     std::map<const void *, TableInfo> tables;
 };
 
@@ -93,6 +96,9 @@ int sonics_create(int device, sonics_ctx **out)
     c->launches = 0;
     c->max_W_last = 0;
     c->dbg = nullptr;
+    c->trace = nullptr;
+    c->trace_len = nullptr;
+    c->trace_cap = 0;
     *out = c;
     return SONICS_OK;
 }
@@ -306,6 +312,10 @@ static int launch_simulate(sonics_ctx *ctx, SimArgs &a, const TableInfo &ti, boo
     cudaStream_t s = (cudaStream_t)stream;
     a.Wcap = ti.max_W;
     a.dbg = ctx->dbg;
+    a.trace = ctx->trace;
+    a.trace_len = ctx->trace_len;
+    a.trace_cap = ctx->trace_cap;
+    auto pcr = ctx->trace ? k_pcr<true> : k_pcr<false>;
     if (!dev_scratch || scratch_bytes < scratch_bytes_for(32, a.Wcap))
         return fail(SONICS_ERR_SPACE, "simulation scratch of %zu bytes is below the minimum %zu", scratch_bytes,
                     scratch_bytes_for(32, a.Wcap));
@@ -318,12 +328,15 @@ static int launch_simulate(sonics_ctx *ctx, SimArgs &a, const TableInfo &ti, boo
     if (wpb < 1)
         return fail(SONICS_ERR_RANGE, "window of %d bins does not fit shared memory", a.Wcap);
     const size_t smem = SONICS_RCP_TABLE * 4 + per_warp * wpb;
-    CUDA_OK(cudaFuncSetAttribute(k_pcr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaFuncSetAttribute(pcr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pcr, wpb * 32, smem));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcr, wpb * 32, smem));
     if (occ < 1)
         occ = 1;
     auto lnl = readout ? k_lnl<true> : k_lnl<false>;
+    if (ctx->trace && total_units > cap_units)
+        return fail(SONICS_ERR_SPACE, "draw trace: %lld simulations do not fit one scratch chunk of %lld",
+                    (long long)total_units, (long long)cap_units);
     for (int64_t u0 = 0; u0 < total_units; u0 += cap_units) {
         const int64_t nu = std::min<int64_t>(cap_units, total_units - u0);
         a.unit_base = u0;
@@ -332,7 +345,7 @@ static int launch_simulate(sonics_ctx *ctx, SimArgs &a, const TableInfo &ti, boo
         // persistent lanes: no more blocks than there are lanes' worth of work
         const int64_t want = (nu + wpb * 32 - 1) / (wpb * 32);
         const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * occ);
-        k_pcr<<<grid, wpb * 32, smem, s>>>(a);
+        pcr<<<grid, wpb * 32, smem, s>>>(a);
         ctx->launches++;
         CUDA_OK(cudaGetLastError());
         const int lgrid = (int)std::min<int64_t>((nu + 127) / 128, (int64_t)ctx->sm_count * 16);
@@ -400,6 +413,18 @@ int sonics_debug_counters(sonics_ctx *ctx, uint64_t *dev_counters)
     if (!ctx)
         return fail(SONICS_ERR_ARG, "sonics_debug_counters: ctx is NULL");
     ctx->dbg = (unsigned long long *)dev_counters;
+    return SONICS_OK;
+}
+
+int sonics_debug_trace(sonics_ctx *ctx, SonicsTraceEntry *dev_trace, int32_t trace_cap, int32_t *dev_trace_len)
+{
+    if (!ctx)
+        return fail(SONICS_ERR_ARG, "sonics_debug_trace: ctx is NULL");
+    if (dev_trace && (trace_cap <= 0 || !dev_trace_len))
+        return fail(SONICS_ERR_ARG, "sonics_debug_trace: trace_cap and dev_trace_len are required with a buffer");
+    ctx->trace = dev_trace;
+    ctx->trace_len = dev_trace ? dev_trace_len : nullptr;
+    ctx->trace_cap = dev_trace ? trace_cap : 0;
     return SONICS_OK;
 }
 

@@ -73,6 +73,9 @@ def to_csr(genotypes):
     return off, (np.concatenate(al) if al else np.zeros(0, np.int32)), (np.concatenate(rd) if rd else np.zeros(0, np.int32))
 
 
+TRACE_DTYPE = np.dtype([("kind", "<i4"), ("n", "<i4"), ("p", "<f4"), ("x", "<i4")])  # SonicsTraceEntry
+
+
 class Table:
     """A genotype table resident in device memory (torch uint8 tensor owned here)."""
 
@@ -134,6 +137,29 @@ class Engine:
         out = self.torch.empty(4 * n_blocks, dtype=self.torch.int32, device=self.device)
         check(self.lib.sonics_debug_philox(self.ctx, seed, sim, uid, stream_id, n_blocks, out.data_ptr()))
         return out.cpu().numpy().view(np.uint32)
+
+    def simulate_traced(self, params, table, sim_count, seed, trace_cap=4096, sim_begin=0):
+        """simulate() through the traced instantiation of K1a (sonics_debug_trace).
+
+        Returns (out, trace, trace_len, pools): out as simulate(simpar=True) returns it (host copies); trace
+        [n_gt, sim_count, trace_cap] records (TRACE_DTYPE: kind, n, p, x); trace_len [n_gt, sim_count];
+        pools [n_gt, sim_count, max_window] int32, the final pools in window coordinates."""
+        t = self.torch
+        units = table.n_gt * int(sim_count)
+        trace = t.zeros(units * trace_cap * TRACE_DTYPE.itemsize, dtype=t.uint8, device=self.device)
+        tlen = t.zeros(units, dtype=t.int32, device=self.device)
+        check(self.lib.sonics_debug_trace(self.ctx, trace.data_ptr(), int(trace_cap), tlen.data_ptr()))
+        try:
+            out = self.simulate(params, table, sim_count, seed, sim_begin=sim_begin, simpar=True, out_offset=0)
+            self.sync()
+        finally:
+            check(self.lib.sonics_debug_trace(self.ctx, None, 0, None))
+        W = table.max_window
+        raw = self._scratch_buf[256:256 + ((units + 31) // 32) * W * 128].cpu().numpy().view(np.int32)
+        pools = raw.reshape(-1, W, 32).transpose(0, 2, 1).reshape(-1, W)[:units]
+        host = {k: v.cpu().numpy() for k, v in out.items()}
+        return (host, trace.cpu().numpy().view(TRACE_DTYPE).reshape(table.n_gt, sim_count, trace_cap),
+                tlen.cpu().numpy().reshape(table.n_gt, sim_count), pools.reshape(table.n_gt, sim_count, W))
 
     def debug_sample(self, kind, n, p, count, seed):
         out = self.torch.empty(count, dtype=self.torch.int32, device=self.device)

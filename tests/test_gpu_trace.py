@@ -1,0 +1,105 @@
+"""Draw-trace replay: the control logic of K1a is bit-exact against the reference's loop.
+
+The RNG stream of the CUDA path differs from the reference's by design, so simulate() cannot be
+compared draw for draw on a seed.  What CAN be compared exactly is everything that is not sampling:
+the traced instantiation of k_pcr (sonics_debug_trace) records every draw a simulation requests --
+Binomial(n, p) / Poisson(lam), in request order -- and its outcome; the oracle then runs the
+reference's one_repeat()/simulate() loop (sonics.pyx:293-337, 397-480) with scripted draws that hand
+out exactly those outcomes.  The replay fails if the loop ever requests a draw of another kind or
+another n than the kernel did, and at the end the integer pools must be identical in every bin (and
+lnL, computed by K1b from that pool, must match the oracle's mvhyperg within 1e-9).  This pins the
+bin walk, the cycle-start snapshot, the same-cycle up-carry, the mol_down gate, the stale-ct quirk
+below the floor, the capture step and the start pool / noise rules exactly; the samplers themselves
+are pinned distributionally in test_gpu_primitives.py."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from sonics_b200 import engine as eng
+from tests.gpu_util import engine
+from tests.util import CFG1, CFG2, CFG3, cfg_from_case
+
+pytestmark = pytest.mark.gpu
+
+
+def window(reads, kw):
+    """(first bin, width) of the kernel's window (sonics_table_build): bins outside can never hold molecules."""
+    nz = np.nonzero(reads)[0]
+    floor_opt, n_cycles = kw.get("floor", 5), kw.get("n_cycles", 24)
+    floor_al = 1 if floor_opt == -1 else max(1, int(nz[0]) - floor_opt)
+    lo = max(floor_al - 1, int(nz[0]) - n_cycles)
+    lo = max(0, min(lo, int(nz[0])))
+    return lo, int(nz[-1]) + n_cycles - lo + 1
+
+
+def replay_all(genotypes, noise, n_sims, seed, **kw):
+    e = engine()
+    params = eng.make_params(**kw)
+    reads = [orc.parse_reads(g) for g in genotypes]
+    table = e.build_table_from_arrays(params, reads, noise)
+    out, trace, tlen, pools = e.simulate_traced(params, table, n_sims, seed, trace_cap=8192)
+    group = out["group"].view(np.uint16)
+    n_draws = 0
+    worst_dp = worst_dlam = 0.0
+    kinds = set()
+    for g, rd in enumerate(reads):
+        cfg = cfg_from_case(noise[g], kw)
+        nz = np.nonzero(rd)[0]
+        A = len(nz)
+        first_idx = int(np.argmax(rd[nz]))
+        lo, W = window(rd, kw)
+        assert W <= pools.shape[2]
+        for j in range(n_sims):
+            n = int(tlen[g, j])
+            assert 0 < n <= trace.shape[2], (g, j, n)
+            script = trace[g, j, :n]
+            assert (script["x"] >= 0).all()
+            i_lo, i_hi = divmod(int(group[g, j]), A)
+            if kw.get("random", False):
+                idx = [i_lo, i_hi]
+            else:
+                assert first_idx in (i_lo, i_hi)
+                idx = [i_hi if i_lo == first_idx else i_lo]
+            rc, rec, pool, used, dp, dlam, epos = orc.replay_script(cfg, rd, out["simpar"][g, j], idx, script)
+            assert rc == 0, "genotype %d sim %d: replay error %d at draw %d of %d: %s" % (
+                g, j, rc, epos, n, script[max(0, epos - 2):epos + 1])
+            assert used == n, (g, j, used, n)
+            gpu_pool = np.zeros_like(pool)
+            gpu_pool[lo:lo + W] = pools[g, j, :W]
+            assert (gpu_pool == pool).all(), (g, j, np.nonzero(gpu_pool != pool)[0])
+            lnl = out["lnL"][g, j]
+            assert lnl == rec["lnL"] or abs(lnl - rec["lnL"]) <= 1e-9 * abs(rec["lnL"]), (g, j, lnl, rec["lnL"])
+            n_draws += n
+            worst_dp, worst_dlam = max(worst_dp, dp), max(worst_dlam, dlam)
+            kinds |= set(np.unique(script["kind"]).tolist())
+    return n_draws, worst_dp, worst_dlam, kinds
+
+
+def test_replay_default_configs():
+    n, dp, dlam, kinds = replay_all([CFG1, CFG2, "3|40;4|25;7|2"], [0.0, 0.0, 0.0], 96, seed=20261019)
+    assert n > 96 * 3 * 300 and kinds == {1, 2}
+    # p of the slip draws: fp32 incremental expm1 on the device vs fp64 pow in the reference
+    assert dp < 2e-5, dp
+    # lam of the capture step: the same C-float arithmetic on both sides (sonics.pyx:414-419)
+    assert dlam == 0.0, dlam
+
+
+def test_replay_noise_and_wide_window():
+    # cfg3: 40 input alleles, 30 cycles, capture at 16, automatic noise coefficient (noise on)
+    rd = orc.parse_reads(CFG3)
+    nc = float(np.float32(orc.auto_noise_coef(rd)))
+    assert nc > 0
+    n, dp, dlam, kinds = replay_all([CFG3], [nc], 48, seed=7, n_cycles=30, capture_cycle=16)
+    assert n > 48 * 2000 and dlam == 0.0 and dp < 5e-5, (n, dp, dlam)
+
+
+@pytest.mark.parametrize("kw", [dict(floor=-1), dict(floor=0), dict(floor=-3), dict(floor=2),
+                                dict(random=True), dict(up_preference=True),
+                                dict(capture_cycle=1), dict(capture_cycle=24), dict(capture_cycle=40),
+                                dict(n_cycles=3, capture_cycle=2), dict(start_copies=1000),
+                                dict(start_copies=7),
+                                dict(efficiency=(0.9, 1.0), n_cycles=8, capture_cycle=4, start_copies=1000),
+                                dict(down=(0, 0.5), up=(0, 0.5)), dict(capture=(-1.9, -1.5))])
+def test_replay_option_matrix(kw):
+    n, dp, dlam, kinds = replay_all([CFG1, "8|50;9|3;14|20", "2|9;3|1"], [0.0, 0.004, 0.0], 64, seed=11, **kw)
+    assert n > 0 and dlam == 0.0 and dp < 1e-4, (n, dp, dlam)

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as orc
-from tests.util import cfg_from_case, load
+from tests.util import CFG1, CFG2, cfg_from_case, load
 
 CASES = load("one_repeat.json")
 
@@ -38,3 +38,29 @@ def test_fast_mode_same_distribution():
     assert ks_2samp(a["lnL"], b["lnL"]).pvalue > 0.001
     fa, fb = (a["lnL"] == -999999).mean(), (b["lnL"] == -999999).mean()
     assert abs(fa - fb) < 4 * np.sqrt(0.25 * 0.75 * 2 / 16000)
+
+
+@pytest.mark.parametrize("kw", [{}, dict(rng_mode=0), dict(floor_opt=-3), dict(floor_opt=-1), dict(random_start=True),
+                                dict(noise_coef=0.004), dict(n_cycles=30, capture_cycle=16)])
+def test_scripted_draws_reproduce_a_sampled_run(kw):
+    """The scripted-draw mode (used by tests/test_gpu_trace.py to replay the kernel's draws): a sampled
+    one_repeat() records its draws; replaying the record reproduces the pool and lnL bit for bit, and a
+    corrupted record is detected."""
+    cfg = orc.make_cfg(**kw)
+    for spec in (CFG1, CFG2):
+        al = orc.parse_reads(spec)
+        nz = np.nonzero(al)[0]
+        for seed in range(4):
+            rec, pool, script = orc.record_script(cfg, al, seed)
+            idx = [int(np.searchsorted(nz, rec["second"]))]
+            if cfg.random_start:
+                idx = [int(np.searchsorted(nz, rec["first"]))] + idx
+            par = (rec["down"], rec["up"], rec["capture"], rec["efficiency"])
+            rc, rec2, pool2, used, dp, dlam, _ = orc.replay_script(cfg, al, par, idx, script)
+            assert rc == 0 and used == len(script) and (pool == pool2).all() and rec["lnL"] == rec2["lnL"]
+            assert dp < 1e-6 and dlam == 0.0  # p stored as float32 in the record
+            if len(script) > 10:
+                bad = script.copy()
+                bad["n"][len(bad) // 2] += 1
+                assert orc.replay_script(cfg, al, par, idx, bad)[0] == 3
+                assert orc.replay_script(cfg, al, par, idx, script[:-1])[0] == 1
