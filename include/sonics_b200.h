@@ -241,10 +241,21 @@ int sonics_debug_sample(sonics_ctx *ctx, int kind, int n, double p, int64_t coun
  * sonics_rows_write writes the output file of run_sonics(): header (sonics:174-207) + one
  * "sample\tblock\tref\t<row>" line (sonics:437) per genotype in input order, rows formatted as
  * monte_carlo() does (sonics.pyx:122-134,208-269) with Python's str(float) number format; verdicts[i]
- * belongs to the i-th simulated genotype.  vcf == NULL: string mode (one row: name, block, "."). */
+ * belongs to the i-th simulated genotype.  vcf == NULL: string mode (one row: name, block, ".").
+ *
+ * Multi-GPU runs share the host work (the reference's Pool.starmap fans out whole genotypes, sonics:216-221;
+ * its single parse and per-row append, sonics:246-343,436, would bound 8 GPUs): sonics_vcf_parse_range
+ * parses the data lines whose first byte lies in [byte_begin, byte_end) (byte_end < 0: end of file; header
+ * lines are read by every range), so ranges that tile the file parse every line exactly once, in order;
+ * sonics_rows_write_part writes one range's rows with or without the header line; sonics_rows_concat joins
+ * the parts in rank order and removes them.  The random choice of --strict 0 is keyed by (seed, line
+ * offset) and does not depend on the tiling. */
 typedef struct sonics_vcf sonics_vcf;
 int sonics_vcf_parse(const char *path, int strict, int one_allele_threshold, double noise_threshold, int monte_carlo,
                      uint64_t seed, sonics_vcf **out);
+int sonics_vcf_parse_range(const char *path, int64_t byte_begin, int64_t byte_end, int strict,
+                           int one_allele_threshold, double noise_threshold, int monte_carlo, uint64_t seed,
+                           sonics_vcf **out);
 void sonics_vcf_free(sonics_vcf *vcf);
 int64_t sonics_vcf_count(const sonics_vcf *vcf, int what);
 int sonics_vcf_fill(const sonics_vcf *vcf, int32_t *allele_off, int32_t *allele, int32_t *reads, float *noise_coef,
@@ -252,6 +263,10 @@ int sonics_vcf_fill(const sonics_vcf *vcf, int32_t *allele_off, int32_t *allele,
 const char *sonics_vcf_warning(const sonics_vcf *vcf, int64_t i);
 int sonics_rows_write(const char *path, const sonics_vcf *vcf, const SonicsVerdict *verdicts, int64_t n_verdicts,
                       int monte_carlo, const char *add_ratios, const char *name, const char *block);
+int sonics_rows_write_part(const char *path, const sonics_vcf *vcf, const SonicsVerdict *verdicts,
+                           int64_t n_verdicts, int monte_carlo, const char *add_ratios, const char *name,
+                           const char *block, int with_header);
+int sonics_rows_concat(const char *path, const char *const *parts, int n_parts);
 
 /* Kernel launches issued by this ctx so far (bench.py's gpu_launches). */
 int64_t sonics_launch_count(sonics_ctx *ctx);

@@ -96,11 +96,16 @@ PROTOTYPES = {
     "sonics_debug_sample": (_I, [_P, _I, _I, ctypes.c_double, _I64, _U64, _P]),
     "sonics_launch_count": (_I64, [_P]),
     "sonics_vcf_parse": (_I, [ctypes.c_char_p, _I, _I, ctypes.c_double, _I, _U64, ctypes.POINTER(_P)]),
+    "sonics_vcf_parse_range": (_I, [ctypes.c_char_p, _I64, _I64, _I, _I, ctypes.c_double, _I, _U64,
+                                    ctypes.POINTER(_P)]),
     "sonics_vcf_free": (None, [_P]),
     "sonics_vcf_count": (_I64, [_P, _I]),
     "sonics_vcf_fill": (_I, [_P, _P, _P, _P, _P, _P]),
     "sonics_vcf_warning": (ctypes.c_char_p, [_P, _I64]),
     "sonics_rows_write": (_I, [ctypes.c_char_p, _P, _P, _I64, _I, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]),
+    "sonics_rows_write_part": (_I, [ctypes.c_char_p, _P, _P, _I64, _I, ctypes.c_char_p, ctypes.c_char_p,
+                                    ctypes.c_char_p, _I]),
+    "sonics_rows_concat": (_I, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), _I]),
 }
 
 _lib = None

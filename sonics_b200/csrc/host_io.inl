@@ -236,19 +236,37 @@ static void format_row(std::string &out, const SonicsVerdict &v, int monte_carlo
 
 extern "C" {
 
-int sonics_vcf_parse(const char *path, int strict, int one_allele_threshold, double noise_threshold, int monte_carlo,
-                     uint64_t seed, sonics_vcf **out)
+/* A data line belongs to the byte range [byte_begin, byte_end) that holds its first byte; '#' lines are
+ * header wherever they stand and are read by every range up to its own end (the sample names come from
+ * "#CHROM").  byte_end < 0: to the end of the file.  Ranges that tile the file therefore parse every data
+ * line exactly once, in file order -- this is how the ranks of a multi-GPU run share the ingest.  The
+ * random choice of --strict 0 is keyed by (seed, offset of the line), so it does not depend on the tiling. */
+int sonics_vcf_parse_range(const char *path, int64_t byte_begin, int64_t byte_end, int strict,
+                           int one_allele_threshold, double noise_threshold, int monte_carlo, uint64_t seed,
+                           sonics_vcf **out)
 {
     if (!path || !out)
         return fail(SONICS_ERR_ARG, "sonics_vcf_parse: NULL argument");
-    std::ifstream in(path);
+    if (byte_begin < 0)
+        return fail(SONICS_ERR_ARG, "sonics_vcf_parse: negative byte offset");
+    std::ifstream in(path, std::ios::binary);
     if (!in)
         return fail(SONICS_ERR_ARG, "sonics_vcf_parse: cannot open %s", path);
     sonics_vcf *V = new sonics_vcf();
-    std::mt19937_64 rng(seed);
     std::string line;
     std::vector<int64_t> hist(SONICS_MAX_ALLELE);
-    while (std::getline(in, line)) {
+    std::mt19937_64 rng;
+    int64_t pos = 0; // offset of the first byte of the next line
+    bool skipped_to_range = byte_begin == 0;
+    while (true) {
+        if (byte_end >= 0 && pos >= byte_end)
+            break;
+        if (!std::getline(in, line))
+            break;
+        const int64_t line_pos = pos;
+        pos += (int64_t)line.size() + 1;
+        if (!line.empty() && line.back() == '\r')
+            line.pop_back();
         if (!line.empty() && line[0] == '#') {
             if (line.rfind("#CHROM", 0) == 0) {
                 auto f = split(line, '\t');
@@ -256,8 +274,20 @@ int sonics_vcf_parse(const char *path, int strict, int one_allele_threshold, dou
             }
             continue;
         }
+        if (!skipped_to_range) {
+            // first data line of the file: the header is complete; jump to the range
+            skipped_to_range = true;
+            if (line_pos < byte_begin) {
+                in.seekg(byte_begin - 1);
+                if (!std::getline(in, line)) // the rest of the line that straddles byte_begin - 1
+                    break;
+                pos = byte_begin + (int64_t)line.size(); // == offset after that line's '\n'
+                continue;
+            }
+        }
         if (line.empty())
             continue;
+        bool rng_ready = false; // --strict 0: seeded per line on first use
         auto f = split(line, '\t');
         if (f.size() < 9) {
             delete V;
@@ -347,6 +377,10 @@ int sonics_vcf_parse(const char *path, int strict, int one_allele_threshold, dou
                         long long fl = off_bp[i] / L;
                         if (off_bp[i] < 0 && off_bp[i] % L != 0)
                             --fl; // floor division
+                        if (!rng_ready) {
+                            rng.seed(seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(line_pos + 1)));
+                            rng_ready = true;
+                        }
                         const long long target = fl + ref + (long long)(rng() & 1u);
                         whole[target] += sup[i];
                     }
@@ -408,6 +442,12 @@ int sonics_vcf_parse(const char *path, int strict, int one_allele_threshold, dou
     return SONICS_OK;
 }
 
+int sonics_vcf_parse(const char *path, int strict, int one_allele_threshold, double noise_threshold, int monte_carlo,
+                     uint64_t seed, sonics_vcf **out)
+{
+    return sonics_vcf_parse_range(path, 0, -1, strict, one_allele_threshold, noise_threshold, monte_carlo, seed, out);
+}
+
 void sonics_vcf_free(sonics_vcf *v) { delete v; }
 
 /* what: 0 parsed genotypes (rows incl. skipped), 1 genotypes to simulate, 2 CSR entries, 3 samples, 4 blocks,
@@ -453,8 +493,9 @@ const char *sonics_vcf_warning(const sonics_vcf *v, int64_t i)
 
 /* Writes <path>: header + one line per parsed genotype that is not skipped, in file order; verdicts[i] belongs
  * to the i-th genotype to simulate.  vcf == NULL: string mode, one row with (name, block, ".") and verdicts[0]. */
-int sonics_rows_write(const char *path, const sonics_vcf *vcf, const SonicsVerdict *verdicts, int64_t n_verdicts,
-                      int monte_carlo, const char *add_ratios, const char *name, const char *block)
+int sonics_rows_write_part(const char *path, const sonics_vcf *vcf, const SonicsVerdict *verdicts,
+                           int64_t n_verdicts, int monte_carlo, const char *add_ratios, const char *name,
+                           const char *block, int with_header)
 {
     if (!path || (!verdicts && n_verdicts > 0))
         return fail(SONICS_ERR_ARG, "sonics_rows_write: NULL argument");
@@ -463,7 +504,8 @@ int sonics_rows_write(const char *path, const sonics_vcf *vcf, const SonicsVerdi
         add_perc = split(add_ratios, ';');
     std::string out;
     out.reserve(1 << 20);
-    out += monte_carlo ? "sample\tblock\tref\tgenotype\tidentity\tidentity_75th_percentile\tr_squared\t"
+    if (with_header)
+        out += monte_carlo ? "sample\tblock\tref\tgenotype\tidentity\tidentity_75th_percentile\tr_squared\t"
                          "r_squared_75th_percentile\tlnL\tlnL_75th_percentile\trepeats\n"
                        : "sample\tblock\tref\tgenotype\tidentity\tr_squared\tlnL\tfilter\tMWUtes_pval\tbest_lnL_ratio\t"
                          "quartile_lnL_ratio\trepeats\tadditional_ratios\n";
@@ -510,6 +552,41 @@ int sonics_rows_write(const char *path, const sonics_vcf *vcf, const SonicsVerdi
     }
     fwrite(out.data(), 1, out.size(), fp);
     fclose(fp);
+    return SONICS_OK;
+}
+
+int sonics_rows_write(const char *path, const sonics_vcf *vcf, const SonicsVerdict *verdicts, int64_t n_verdicts,
+                      int monte_carlo, const char *add_ratios, const char *name, const char *block)
+{
+    return sonics_rows_write_part(path, vcf, verdicts, n_verdicts, monte_carlo, add_ratios, name, block, 1);
+}
+
+/* Concatenates the part files (in the order given) into <path> and removes them. */
+int sonics_rows_concat(const char *path, const char *const *parts, int n_parts)
+{
+    if (!path || (!parts && n_parts > 0))
+        return fail(SONICS_ERR_ARG, "sonics_rows_concat: NULL argument");
+    FILE *fo = fopen(path, "wb");
+    if (!fo)
+        return fail(SONICS_ERR_ARG, "sonics_rows_concat: cannot open %s", path);
+    std::vector<char> buf(4 << 20);
+    for (int i = 0; i < n_parts; ++i) {
+        FILE *fi = fopen(parts[i], "rb");
+        if (!fi) {
+            fclose(fo);
+            return fail(SONICS_ERR_ARG, "sonics_rows_concat: cannot open %s", parts[i]);
+        }
+        size_t n;
+        while ((n = fread(buf.data(), 1, buf.size(), fi)) > 0)
+            if (fwrite(buf.data(), 1, n, fo) != n) {
+                fclose(fi);
+                fclose(fo);
+                return fail(SONICS_ERR_SPACE, "sonics_rows_concat: short write to %s", path);
+            }
+        fclose(fi);
+        remove(parts[i]);
+    }
+    fclose(fo);
     return SONICS_OK;
 }
 

@@ -8,16 +8,19 @@ rule of process_one_genotype (sonics:353-419), `--strict` handling in the VCF
 parser (sonics:311-334) and the row format (via sonics_b200.sonics.format_row).
 
 What changes: genotypes are gathered first, pre-filtered on the host, then run
-through sonics_genotype_batch in chunks; with --gpus N (or under torchrun) the
-list is split into contiguous shards, one process per GPU, and the rows are
-written once, in input order, by rank 0 (the reference appends from pool workers
-in completion order, sonics:436).
+through sonics_genotype_batch in chunks.  Under torchrun (one process per GPU)
+the ranks share everything: each parses the lines of its byte range of the VCF,
+simulates them and writes its rows; rank 0 joins the parts in rank order, so the
+file is in input order (the reference appends from pool workers in completion
+order, sonics:436).  With --gpus N in one process the list is split into
+contiguous shards and the rows are written once by the parent.
 """
 import argparse
 import logging
 import os
 import re
 import sys
+import time
 
 import numpy as np
 
@@ -206,6 +209,9 @@ def prefilter(input_tuple, constants, options):
     return "sim", (alleles, float(noise_coef))
 
 
+LAST_TIMINGS = {}  # seconds of the last run_sonics() in this process: ingest / simulate / write (tools/scale_vcf.py)
+
+
 def shard_bounds(n, world, rank):
     """Contiguous shard [lo, hi) of n work items for `rank` of `world` (sizes differ by at most one)."""
     base, rem = divmod(n, world)
@@ -229,23 +235,6 @@ def run_batch_verdicts(allele_off, allele, reads, noise, constants, ranges, opti
         parts.append(e.genotype_batch(params, off, allele[a0:a1], reads[a0:a1], noise[c0:c1], options["repetitions"],
                                       seed, uid=uids))
     return np.concatenate(parts) if parts else np.zeros(0, dtype=eng.VERDICT_DTYPE)
-
-
-def sharded(n, compute_shard, world=None, rank=None):
-    """One process per GPU under torchrun: rank r computes compute_shard(lo, hi) for its contiguous shard of the
-    n work items; rank 0 receives the parts in rank order (host-side gather_object, ~170 B per genotype -- there is
-    no collective on the data path).  Returns the list of parts on rank 0 and None elsewhere."""
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else world
-    rank = int(os.environ.get("RANK", "0")) if rank is None else rank
-    if not dist.is_initialized():
-        import torch
-        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
-    lo, hi = shard_bounds(n, world, rank)
-    part = compute_shard(lo, hi)
-    gathered = [None] * world if rank == 0 else None
-    dist.gather_object(part, gathered, dst=0)
-    return gathered
 
 
 def _csr_slice(allele_off, allele, reads, noise, lo, hi):
@@ -274,7 +263,10 @@ def run_sonics(feed_in, constants, ranges, options, seed=None, gpus=1, chunk=655
         seed = int.from_bytes(os.urandom(8), "little")
     if options["save_report"]:
         return _run_sonics_per_genotype(feed_in, constants, ranges, options, seed, out_file_path)
+    if options["vcf_mode"] and world > 1:
+        return _run_vcf_ranks(feed_in, constants, ranges, options, seed, chunk, out_file_path, rank, world)
     vcf = None
+    t0 = time.time()
     if options["vcf_mode"]:
         vcf = hostio.Vcf(feed_in, options["strict"], constants["one_allele_threshold"], constants["noise_threshold"],
                          options["monte_carlo"], seed)
@@ -282,6 +274,8 @@ def run_sonics(feed_in, constants, ranges, options, seed=None, gpus=1, chunk=655
             raise Exception("No valid genotype after parsing VCF file.")
         off, al, rd, nz = vcf.allele_off, vcf.allele, vcf.reads, vcf.noise_coef
     else:
+        if rank != 0:
+            return
         kind, payload = prefilter((options["name"], options["block"], ".", feed_in), constants, options)
         if kind == "skip":
             hostio.write_rows(out_file_path, np.zeros(0, dtype=hostio.VERDICT_DTYPE), None, options["monte_carlo"],
@@ -296,14 +290,8 @@ def run_sonics(feed_in, constants, ranges, options, seed=None, gpus=1, chunk=655
         off, al, rd = eng.to_csr([payload[0]])
         nz = np.array([payload[1]], dtype=np.float32)
     n = len(nz)
-    if world > 1:
-        local = int(os.environ.get("LOCAL_RANK", rank))
-        parts = sharded(n, lambda lo, hi: run_batch_verdicts(*_csr_slice(off, al, rd, nz, lo, hi), constants, ranges,
-                                                             options, seed, local, chunk, lo), world, rank)
-        if rank != 0:
-            return
-        verdicts = np.concatenate(parts)
-    elif gpus > 1:
+    t1 = time.time()
+    if gpus > 1:
         import multiprocessing as mp
         jobs = []
         for r in range(gpus):
@@ -313,8 +301,52 @@ def run_sonics(feed_in, constants, ranges, options, seed=None, gpus=1, chunk=655
             verdicts = np.concatenate(pool.map(_verdict_shard_worker, jobs))
     else:
         verdicts = run_batch_verdicts(off, al, rd, nz, constants, ranges, options, seed, 0, chunk)
+    t2 = time.time()
     hostio.write_rows(out_file_path, verdicts, vcf, options["monte_carlo"], options["add_ratios"], options["name"],
                       options["block"])
+    LAST_TIMINGS.update(ingest=t1 - t0, simulate=t2 - t1, write=time.time() - t2, join=0.0, genotypes=int(n))
+
+
+def _run_vcf_ranks(feed_in, constants, ranges, options, seed, chunk, out_file_path, rank, world, compute=None):
+    """VCF mode under torchrun, one process per GPU: the ranks share ingest, simulation and output.
+
+    Rank r parses the data lines that start in its byte range of the file (hostio.byte_ranges), learns the
+    number of genotypes before its range from one all_gather of counts (the RNG is keyed by the genotype's
+    position in the whole file, so the rows do not depend on the number of ranks), runs its genotypes on
+    its GPU, and writes its rows to <out>.part<r>; rank 0 joins the parts in rank order.  No collective
+    touches the data path.  `compute` replaces the GPU call in the CPU (gloo) test of this plumbing."""
+    import torch.distributed as dist
+    from . import hostio
+    if not dist.is_initialized():
+        import torch
+        if torch.cuda.is_available():
+            local = int(os.environ.get("LOCAL_RANK", rank))
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo")
+    t0 = time.time()
+    vcf = hostio.Vcf(feed_in, options["strict"], constants["one_allele_threshold"], constants["noise_threshold"],
+                     options["monte_carlo"], seed, byte_range=hostio.byte_ranges(feed_in, world)[rank])
+    t1 = time.time()
+    counts = [None] * world
+    dist.all_gather_object(counts, (vcf.n_rows, vcf.n_sim))
+    if sum(c[0] for c in counts) == 0:
+        raise Exception("No valid genotype after parsing VCF file.")
+    uid0 = sum(c[1] for c in counts[:rank])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    compute = compute or (lambda off, al, rd, nz, uid_offset: run_batch_verdicts(
+        off, al, rd, nz, constants, ranges, options, seed, local, chunk, uid_offset))
+    t2 = time.time()
+    verdicts = compute(vcf.allele_off, vcf.allele, vcf.reads, vcf.noise_coef, uid0)
+    t3 = time.time()
+    hostio.write_rows("%s.part%d" % (out_file_path, rank), verdicts, vcf, options["monte_carlo"],
+                      options["add_ratios"], options["name"], options["block"], header=(rank == 0))
+    t4 = time.time()
+    dist.barrier()
+    if rank == 0:
+        hostio.concat_parts(out_file_path, ["%s.part%d" % (out_file_path, r) for r in range(world)])
+    LAST_TIMINGS.update(ingest=t1 - t0, simulate=t3 - t2, write=t4 - t3, join=time.time() - t4, genotypes=int(vcf.n_sim))
 
 
 def _run_sonics_per_genotype(feed_in, constants, ranges, options, seed, out_file_path):

@@ -13,12 +13,16 @@ from .engine import VERDICT_DTYPE
 class Vcf:
     """Parsed lobSTR VCF: CSR of the genotypes to simulate + per-row kinds (0 skip, 1 no_simulations, 2 simulate)."""
 
-    def __init__(self, path, strict=1, one_allele_threshold=45, noise_threshold=0.05, monte_carlo=False, seed=0):
+    def __init__(self, path, strict=1, one_allele_threshold=45, noise_threshold=0.05, monte_carlo=False, seed=0,
+                 byte_range=None):
+        """byte_range=(begin, end): only the data lines whose first byte lies in [begin, end) (end < 0: to the end
+        of the file); ranges that tile the file parse every line exactly once (one range per rank)."""
         self.lib = _abi.load()
         h = ctypes.c_void_p()
-        check(self.lib.sonics_vcf_parse(str(path).encode(), int(strict), int(one_allele_threshold),
-                                        float(noise_threshold), int(bool(monte_carlo)), int(seed) & (2**64 - 1),
-                                        ctypes.byref(h)))
+        b0, b1 = (0, -1) if byte_range is None else (int(byte_range[0]), int(byte_range[1]))
+        check(self.lib.sonics_vcf_parse_range(str(path).encode(), b0, b1, int(strict), int(one_allele_threshold),
+                                              float(noise_threshold), int(bool(monte_carlo)),
+                                              int(seed) & (2**64 - 1), ctypes.byref(h)))
         self.handle = h
         c = lambda w: int(self.lib.sonics_vcf_count(h, w))
         self.n_rows, self.n_sim, n_entries, self.n_samples, self.n_blocks, n_warn = (c(i) for i in range(6))
@@ -45,9 +49,26 @@ class Vcf:
             pass
 
 
-def write_rows(path, verdicts, vcf=None, monte_carlo=False, add_ratios="", name="sample", block="Block"):
-    """Header + rows of run_sonics() (sonics:174-207, :437); verdicts: structured array (VERDICT_DTYPE)."""
+def write_rows(path, verdicts, vcf=None, monte_carlo=False, add_ratios="", name="sample", block="Block", header=True):
+    """Header + rows of run_sonics() (sonics:174-207, :437); verdicts: structured array (VERDICT_DTYPE).
+    header=False writes the rows only (a part of a multi-rank run, see concat_parts)."""
     lib = _abi.load()
     v = np.ascontiguousarray(verdicts, dtype=VERDICT_DTYPE)
-    check(lib.sonics_rows_write(str(path).encode(), vcf.handle if vcf is not None else None, v.ctypes.data, len(v),
-                                int(bool(monte_carlo)), add_ratios.encode(), name.encode(), block.encode()))
+    check(lib.sonics_rows_write_part(str(path).encode(), vcf.handle if vcf is not None else None, v.ctypes.data,
+                                     len(v), int(bool(monte_carlo)), add_ratios.encode(), name.encode(),
+                                     block.encode(), int(bool(header))))
+
+
+def byte_ranges(path, world):
+    """[begin, end) per rank: equal byte shares of the file (the parser assigns each line to the range that
+    holds its first byte)."""
+    import os
+    size = os.path.getsize(path)
+    return [(r * size // world, (r + 1) * size // world if r + 1 < world else -1) for r in range(world)]
+
+
+def concat_parts(path, parts):
+    """Join the per-rank part files, in rank order, into the output file; the parts are removed."""
+    lib = _abi.load()
+    arr = (ctypes.c_char_p * len(parts))(*[str(p).encode() for p in parts])
+    check(lib.sonics_rows_concat(str(path).encode(), arr, len(parts)))

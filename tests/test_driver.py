@@ -118,37 +118,44 @@ WORKER = textwrap.dedent("""
     sys.path.insert(0, %r)
     import numpy as np
     import torch.distributed as dist
-    from sonics_b200 import driver
+    from sonics_b200 import driver, hostio
+    vcf_path, out_path = sys.argv[1], sys.argv[2]
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    off = np.array([0, 2, 5, 7, 9, 12, 14, 16, 19, 21, 23, 25], dtype=np.int32)  # 11 genotypes, ragged
-    al = np.arange(25, dtype=np.int32); rd = al + 1; nz = np.linspace(0, 1, 11).astype(np.float32)
-    def shard(lo, hi):
-        o, a, r, z = driver._csr_slice(off, al, rd, nz, lo, hi)
-        assert o[0] == 0 and o[-1] == len(a) == len(r) and len(z) == hi - lo
-        return [(lo + k, int(a[o[k]]), rank) for k in range(hi - lo)]   # (global position = RNG uid, first allele, rank)
-    parts = driver.sharded(11, shard)
+    def compute(off, al, rd, nz, uid0):   # stands in for the GPU: a verdict that encodes (uid, first allele, reads)
+        v = np.zeros(len(nz), dtype=hostio.VERDICT_DTYPE)
+        v["allele_lo"] = al[off[:-1]]
+        v["allele_hi"] = al[off[1:] - 1]
+        v["filter"] = 1
+        v["run_reps"] = uid0 + np.arange(len(nz))
+        v["lnL"] = -np.add.reduceat(rd, off[:-1]).astype(np.float64) if len(nz) else 0
+        return v
+    constants = {"one_allele_threshold": 45, "noise_threshold": 0.05}
+    options = {"strict": 1, "monte_carlo": False, "add_ratios": "", "name": "sample", "block": "Block"}
+    driver._run_vcf_ranks(vcf_path, constants, None, options, 5, 65536, out_path, rank, world, compute=compute)
+    dist.barrier()
     if rank == 0:
-        rows = [x for p in parts for x in p]
-        assert [x[0] for x in rows] == list(range(11)), rows
-        assert [x[1] for x in rows] == [int(al[off[g]]) for g in range(11)], rows
-        assert rows[0][2] == 0 and rows[-1][2] == 1
-        print("GATHER_OK")
-    else:
-        assert parts is None
+        whole = hostio.Vcf(vcf_path)
+        hostio.write_rows(out_path + ".single", compute(whole.allele_off, whole.allele, whole.reads, whole.noise_coef, 0),
+                          whole)
+        assert open(out_path).read() == open(out_path + ".single").read()
+        assert not os.path.exists(out_path + ".part0") and not os.path.exists(out_path + ".part1")
+        print("RANKS_OK", whole.n_sim)
     dist.destroy_process_group()
 """)
 
 
-def test_two_rank_gloo_shard_and_gather():
-    """N > 1 host path on CPU: contiguous shards, uid = global position, ordered gather on rank 0."""
-    with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as f:
-        f.write(WORKER % ROOT)
-    try:
-        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                              "--master-addr", "127.0.0.1", "--master-port", "29631", f.name],
-                             capture_output=True, text=True, timeout=240)
-        assert out.returncode == 0, out.stderr[-2000:]
-        assert "GATHER_OK" in out.stdout
-    finally:
-        os.unlink(f.name)
+def test_two_rank_gloo_vcf_ingest_simulate_write(tmp_path):
+    """N > 1 host path on CPU (gloo, 2 ranks): byte-range ingest, uid = position in the whole file, per-rank part
+    files joined in rank order == the single-process output (the GPU call is replaced by a stub)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import synth_vcf
+    vcf = str(tmp_path / "in.vcf")
+    synth_vcf.write_vcf(vcf, synth_vcf.make_genotypes(23, 3, seed=4, cov=(20, 300), noisy=0.3), 3)
+    worker = str(tmp_path / "worker.py")
+    open(worker, "w").write(WORKER % ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29631", worker, vcf,
+                          str(tmp_path / "out.txt")], capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "RANKS_OK" in out.stdout

@@ -124,3 +124,80 @@ def test_rows_writer_vcf_mode_order_and_no_simulations(tmp_path):
     assert lines[3].startswith("c\tL2\t20\t20/21\t") and len(lines) == 4
     with pytest.raises(Exception, match="verdicts for more genotypes"):
         hostio.write_rows(out, v[:2], vcf)
+
+
+def _csr(v):
+    return (v.n_rows, v.n_sim, list(v.allele_off), list(v.allele), list(v.reads), list(v.noise_coef), list(v.row_kind))
+
+
+def _join(parts):
+    """Concatenate the CSR pieces of consecutive ranges the way the ranks' global numbering sees them."""
+    n_rows = sum(p[0] for p in parts)
+    n_sim = sum(p[1] for p in parts)
+    off, al, rd, nz, kind = [0], [], [], [], []
+    for p in parts:
+        base = off[-1]
+        off += [base + o for o in p[2][1:]]
+        al += p[3]
+        rd += p[4]
+        nz += p[5]
+        kind += p[6]
+    return (n_rows, n_sim, off, al, rd, nz, kind)
+
+
+@pytest.mark.parametrize("strict", [0, 1, 2])
+def test_byte_range_tilings_parse_every_line_once(tmp_path, strict):
+    """Multi-GPU ingest: any tiling of the file into byte ranges yields the whole-file parse, in order, including
+    cuts inside the header, at line starts, inside lines, CRLF endings and a last line without newline; the
+    random choice of --strict 0 does not depend on the tiling."""
+    import synth_vcf
+    p = str(tmp_path / "t.vcf")
+    loci = synth_vcf.make_genotypes(7, 3, seed=5, cov=(20, 300), noisy=0.3)
+    synth_vcf.write_vcf(p, loci, 3)
+    text = open(p).read()
+    # partial-repeat offsets (exercise --strict), a comment line inside the data, CRLF, no final newline
+    lines = text.rstrip("\n").split("\n")
+    lines[3] = lines[3].replace("0/0:", "0/0:1|7;", 1)
+    lines.insert(5, "# a comment between data lines")
+    lines[6] += "\r"
+    open(p, "w", newline="").write("\n".join(lines))
+    size = os.path.getsize(p)
+    whole = hostio.Vcf(p, strict, seed=77)
+    ref = _csr(whole)
+    assert ref[0] > 0 and ref[1] > 0
+    cuts = sorted(set(list(range(0, size + 1, 13)) + [text.index("locus1\t"), text.index("locus2\t"),
+                                                      text.index("locus2\t") - 1, text.index("locus2\t") + 1, size]))
+    for c in cuts:  # two ranges [0, c) [c, end)
+        a = hostio.Vcf(p, strict, seed=77, byte_range=(0, c))
+        b = hostio.Vcf(p, strict, seed=77, byte_range=(c, -1))
+        assert _join([_csr(a), _csr(b)]) == ref, c
+    for world in (3, 4, 8, 64):
+        parts = [_csr(hostio.Vcf(p, strict, seed=77, byte_range=r)) for r in hostio.byte_ranges(p, world)]
+        assert _join(parts) == ref, world
+
+
+def test_part_files_concatenate_to_the_whole_output(tmp_path):
+    import synth_vcf
+    p = str(tmp_path / "t.vcf")
+    synth_vcf.write_vcf(p, synth_vcf.make_genotypes(9, 4, seed=6, cov=(20, 300), noisy=0.3), 4)
+    whole = hostio.Vcf(p)
+    rs = np.random.RandomState(3)
+    verdicts = np.zeros(whole.n_sim, dtype=hostio.VERDICT_DTYPE)
+    verdicts["allele_lo"] = rs.randint(5, 20, whole.n_sim)
+    verdicts["allele_hi"] = verdicts["allele_lo"] + rs.randint(0, 3, whole.n_sim)
+    verdicts["filter"] = 1
+    verdicts["lnL"] = -rs.rand(whole.n_sim) * 50
+    verdicts["identity"] = rs.rand(whole.n_sim)
+    verdicts["run_reps"] = 100
+    hostio.write_rows(str(tmp_path / "whole.txt"), verdicts, whole)
+    parts, lo = [], 0
+    for r, br in enumerate(hostio.byte_ranges(p, 3)):
+        v = hostio.Vcf(p, byte_range=br)
+        part = str(tmp_path / ("part%d" % r))
+        hostio.write_rows(part, verdicts[lo:lo + v.n_sim], v, header=(r == 0))
+        lo += v.n_sim
+        parts.append(part)
+    assert lo == whole.n_sim
+    hostio.concat_parts(str(tmp_path / "joined.txt"), parts)
+    assert open(tmp_path / "joined.txt").read() == open(tmp_path / "whole.txt").read()
+    assert not any(os.path.exists(q) for q in parts)

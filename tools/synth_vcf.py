@@ -53,12 +53,14 @@ def make_genotypes(n_loci, n_samples, seed=20261019, cov=(50, 1000), noisy=0.0):
     return loci
 
 
-def write_vcf(path, loci, n_samples):
+def write_vcf(path, loci, n_samples, start=0, header=True):
+    """start: number of loci before these (names / positions continue); header=False: data lines only."""
     with open(path, "w") as f:
-        f.write("##fileformat=VCFv4.1\n")
-        f.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" +
-                "\t".join("sample%d" % (i + 1) for i in range(n_samples)) + "\n")
-        for li, (L, R, motif, samples) in enumerate(loci):
+        if header:
+            f.write("##fileformat=VCFv4.1\n")
+            f.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" +
+                    "\t".join("sample%d" % (i + 1) for i in range(n_samples)) + "\n")
+        for li, (L, R, motif, samples) in enumerate(loci, start):
             cols = []
             for reads in samples:
                 allreads = ";".join("%d|%d" % ((a - R) * L, c) for a, c in reads)
