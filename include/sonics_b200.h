@@ -201,7 +201,10 @@ int sonics_genotype_batch(sonics_ctx *ctx, const SonicsParams *params, int n_gt,
                           size_t dev_work_bytes, void *stream);
 
 /* ---- test hooks (unit tests of the device RNG and samplers) ---------------
- * sonics_debug_philox:  n_blocks x 4 u32 of the Philox4x32-10 stream (seed; sim, uid, stream).
+ * sonics_debug_philox:  n_blocks x 4 u32 of the Philox4x32-10 stream (seed; sim, uid, stream): priors, start
+ *                       alleles, readout.
+ * sonics_debug_pairs:   n_pairs x 2 u32 of the Philox2x32-10 stream the PCR cycles draw from
+ *                       (key = sim_lo ^ seed_lo, counter = (pair index | sim_hi << 24, uid ^ seed_hi)).
  * sonics_debug_sample:  count draws, one per thread (thread t uses sim = t), of
  *      kind 0: Binomial(n, p)    kind 1: Poisson(lam = p)
  * into dev_out (int32).  Both synchronous; dev_out is caller-owned device memory. */
@@ -228,6 +231,7 @@ typedef struct {
 int sonics_debug_trace(sonics_ctx *ctx, SonicsTraceEntry *dev_trace, int32_t trace_cap, int32_t *dev_trace_len);
 int sonics_debug_philox(sonics_ctx *ctx, uint64_t seed, uint64_t sim, uint32_t uid, uint32_t stream_id, int n_blocks,
                         uint32_t *dev_out);
+int sonics_debug_pairs(sonics_ctx *ctx, uint64_t seed, uint64_t sim, uint32_t uid, int n_pairs, uint32_t *dev_out);
 int sonics_debug_sample(sonics_ctx *ctx, int kind, int n, double p, int64_t count, uint64_t seed, int32_t *dev_out);
 
 /* ---- native host I/O (no GPU involved) ----------------------------------------------------------

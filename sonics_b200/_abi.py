@@ -93,6 +93,7 @@ PROTOTYPES = {
     "sonics_debug_counters": (_I, [_P, _P]),
     "sonics_debug_trace": (_I, [_P, _P, ctypes.c_int32, _P]),
     "sonics_debug_philox": (_I, [_P, _U64, _U64, ctypes.c_uint32, ctypes.c_uint32, _I, _P]),
+    "sonics_debug_pairs": (_I, [_P, _U64, _U64, ctypes.c_uint32, _I, _P]),
     "sonics_debug_sample": (_I, [_P, _I, _I, ctypes.c_double, _I64, _U64, _P]),
     "sonics_launch_count": (_I64, [_P]),
     "sonics_vcf_parse": (_I, [ctypes.c_char_p, _I, _I, ctypes.c_double, _I, _U64, ctypes.POINTER(_P)]),

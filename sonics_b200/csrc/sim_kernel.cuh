@@ -171,6 +171,17 @@ __global__ void k_debug_philox(uint64_t seed, uint64_t sim, uint32_t uid, uint32
     }
 }
 
+__global__ void k_debug_pairs(uint64_t seed, uint64_t sim, uint32_t uid, int n_pairs, uint32_t *out)
+{
+    PairRng r;
+    r.init(seed, sim, uid);
+    for (int i = 0; i < n_pairs; ++i) {
+        const uint2 v = r.pair();
+        out[2 * i + 0] = v.x;
+        out[2 * i + 1] = v.y;
+    }
+}
+
 __global__ void k_debug_sample(int kind, int n, double p, int64_t count, uint64_t seed, int32_t *out)
 {
     __shared__ float rcp_tab[SONICS_RCP_TABLE];
@@ -241,8 +252,8 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
     int mode = M_BOUND, pc = PC_NEWSIM;
     int u = -1; // work unit in flight
     int W = 0, lo = 0, floor_bin = 0;
-    Rng rng;
-    rng.init(a.seed, 0, 0, STREAM_MAIN);
+    PairRng rng;
+    rng.init(a.seed, 0, 0);
     float eff = 0.f, capture = 0.f, l_up = 0.f, l_dn = 0.f, e1_up = 0.f, e1_dn = 0.f;
     int live_lo = 0, live_hi = -1;
     int cycle = 1;
@@ -308,8 +319,10 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
                             floor_bin = h.floor_al - lo;
                             const int A = h.n_alleles;
                             // generate_params (sonics.pyx:33-45): d, u, c, p in that order
-                            rng.init(a.seed, (uint64_t)j, h.uid, STREAM_MAIN);
-                            const uint4 q0 = rng.block4(), q1 = rng.block4(), q2 = rng.block4();
+                            Rng prior;
+                            prior.init(a.seed, (uint64_t)j, h.uid, STREAM_MAIN);
+                            const uint4 q0 = prior.block4(), q1 = prior.block4(), q2 = prior.block4();
+                            rng.init(a.seed, (uint64_t)j, h.uid); // the draws of the PCR cycles
                             const double par_down = a.p.down_lo + a.p.down_rng * u01_53(q0.x, q0.y);
                             const double par_up = a.p.up_preference
                                                       ? a.p.up_lo + (a.p.up_hi - a.p.up_lo) * u01_53(q0.z, q0.w)
@@ -577,14 +590,14 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
         // bounded chunks of the sequential search: stragglers continue in the next INV run together
         // with the newcomers).  Lanes in a rejection sampler run ONE trial per pass (an immediate
         // retry would execute with ~1 lane).  Every lane that consumes randomness in this pass takes
-        // the next 128-bit block of ITS OWN simulation's stream -- the block counter advances only
+        // the next 64-bit block of ITS OWN simulation's stream -- the block counter advances only
         // when the simulation consumes, never with the warp's pass count -- through one call site.
         {
             const unsigned m_inv = __ballot_sync(SONICS_FULL, mode == M_INV0 || mode == M_INVRUN);
             const bool run_inv = __popc(m_inv) >= SONICS_THR_INV || (m_inv != 0u && m_busy == 0u);
-            uint4 words = make_uint4(0u, 0u, 0u, 0u);
+            uint2 words = make_uint2(0u, 0u);
             if (mode == M_BTRS || mode == M_POIS || (run_inv && mode == M_INV0))
-                words = rng.block4();
+                words = rng.pair();
             if (run_inv && (mode == M_INV0 || mode == M_INVRUN)) {
                 if (mode == M_INV0) {
                     inv_setup(ds, dn, ds.p);

@@ -441,6 +441,18 @@ int sonics_debug_philox(sonics_ctx *ctx, uint64_t seed, uint64_t sim, uint32_t u
     return SONICS_OK;
 }
 
+int sonics_debug_pairs(sonics_ctx *ctx, uint64_t seed, uint64_t sim, uint32_t uid, int n_pairs, uint32_t *dev_out)
+{
+    if (!ctx || !dev_out || n_pairs <= 0)
+        return fail(SONICS_ERR_ARG, "sonics_debug_pairs: bad argument");
+    CUDA_OK(cudaSetDevice(ctx->device));
+    k_debug_pairs<<<1, 1>>>(seed, sim, uid, n_pairs, dev_out);
+    ctx->launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaDeviceSynchronize());
+    return SONICS_OK;
+}
+
 int sonics_debug_sample(sonics_ctx *ctx, int kind, int n, double p, int64_t count, uint64_t seed, int32_t *dev_out)
 {
     if (!ctx || !dev_out || count <= 0 || (kind != 0 && kind != 1))

@@ -138,6 +138,11 @@ class Engine:
         check(self.lib.sonics_debug_philox(self.ctx, seed, sim, uid, stream_id, n_blocks, out.data_ptr()))
         return out.cpu().numpy().view(np.uint32)
 
+    def debug_pairs(self, seed, sim, uid, n_pairs):
+        out = self.torch.empty(2 * n_pairs, dtype=self.torch.int32, device=self.device)
+        check(self.lib.sonics_debug_pairs(self.ctx, seed, sim, uid, n_pairs, out.data_ptr()))
+        return out.cpu().numpy().view(np.uint32)
+
     def simulate_traced(self, params, table, sim_count, seed, trace_cap=4096, sim_begin=0):
         """simulate() through the traced instantiation of K1a (sonics_debug_trace).
 

@@ -27,6 +27,17 @@ def philox4x32_10(ctr, key):
     return c
 
 
+def philox2x32_10(ctr, key):
+    """Pure-Python Philox2x32-10 (same paper): the stream of the PCR cycles' draws."""
+    c0, c1 = ctr
+    k = key
+    for _ in range(10):
+        p = 0xD256D193 * c0
+        c0, c1 = ((p >> 32) ^ k ^ c1) & 0xFFFFFFFF, p & 0xFFFFFFFF
+        k = (k + 0x9E3779B9) & 0xFFFFFFFF
+    return [c0, c1]
+
+
 def gpu_lnl_by_group(e, genotype, n_sims, seed, noise_coef=0.0, **pkw):
     """Run n_sims simulations of one genotype; returns {label: lnL array}, table."""
     params = eng.make_params(**pkw)

@@ -4,7 +4,7 @@ import pytest
 import scipy.stats as st
 
 from oracle import oracle as orc
-from tests.gpu_util import engine, philox4x32_10
+from tests.gpu_util import engine, philox2x32_10, philox4x32_10
 from tests.util import load
 
 pytestmark = pytest.mark.gpu
@@ -16,6 +16,23 @@ def test_philox_reference_vectors():
     assert philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_philox2x32_reference_vectors_and_device_stream():
+    # Random123 known-answer vectors for philox2x32-10
+    assert philox2x32_10([0, 0], 0) == [0xff1dae59, 0x6cd10df2]
+    assert philox2x32_10([0xffffffff, 0xffffffff], 0xffffffff) == [0x2c3f628b, 0xab4fd7ad]
+    assert philox2x32_10([0x243f6a88, 0x85a308d3], 0x13198a2e) == [0xdd7ce038, 0xf62a4c12]
+    e = engine()
+    assert list(e.debug_pairs(0, 0, 0, 1)) == [0xff1dae59, 0x6cd10df2]
+    seed, sim, uid = 0x299f31d0a4093822, (5 << 32) | 0x85a308d3, 0x13198a2e
+    exp = []
+    for i in range(4):
+        exp += philox2x32_10([i | (5 << 24), uid ^ (seed >> 32)], (sim ^ seed) & 0xffffffff)
+    assert list(e.debug_pairs(seed, sim, uid, 4)) == exp
+    # distinct simulations / genotypes never share a stream (the keying is a bijection of (uid, sim))
+    a = e.debug_pairs(7, 1, 2, 2)
+    assert list(a) != list(e.debug_pairs(7, 2, 1, 2)) and list(a) != list(e.debug_pairs(7, 1, 3, 2))
 
 
 def test_device_philox_stream_layout():
