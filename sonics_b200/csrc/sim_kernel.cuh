@@ -227,12 +227,14 @@ enum { PC_NEWSIM = 0, PC_RESULT = 1, PC_CAPRESULT = 2, PC_SCAN = 3 };
 #define SONICS_INV_CHUNK 32 // sequential-search steps per pass (a bound, rarely reached: n*p < 10)
 #endif
 #ifndef SONICS_PCR_MIN_BLOCKS
-#define SONICS_PCR_MIN_BLOCKS 8
+#define SONICS_PCR_MIN_BLOCKS 7 // x 128 threads x 72 registers; 8 x 64 spills 80 B per thread and is 1.6 % slower
 #endif
 
 // ---------------------------------------------------------------------------------------------
 // K1a
 // ---------------------------------------------------------------------------------------------
+// TRACE: the instrumented instantiation (control-flow counters of sonics_debug_counters and the draw trace
+// of sonics_debug_trace); the production instantiation carries neither (the counters alone cost 5 %).
 template <bool TRACE>
 __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArgs a)
 {
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
                         if (cycle > n_cycles) { // simulation finished: hand the pool to K1b
                             for (int c = 0; c < W; ++c)
                                 a.pool[pool_index(u, Wcap, c)] = hist[c * 32];
-                            if (TRACE)
+                            if (TRACE && a.trace)
                                 a.trace_len[u] = tr_n;
                             pc = PC_NEWSIM;
                         }
@@ -422,13 +424,13 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
         }
 
         // ================= ADVANCE =================
-        if (a.dbg)
+        if (TRACE && a.dbg)
             c_adv_lanes += __popc(__ballot_sync(SONICS_FULL, mode == M_ADV));
         const unsigned m_adv = __ballot_sync(SONICS_FULL, mode == M_ADV);
         if (mode == M_ADV) {
             int req = 0; // 1: binomial(dn, dp)   2: poisson(lam)
             float dp = 0.0f, lam = 0.0f;
-            if (TRACE && (pc == PC_RESULT || pc == PC_CAPRESULT) && tr_n <= a.trace_cap)
+            if (TRACE && a.trace && (pc == PC_RESULT || pc == PC_CAPRESULT) && tr_n <= a.trace_cap)
                 a.trace[(size_t)u * a.trace_cap + tr_n - 1].x = x;
             // ---- (1) consume the finished draw ----
             // Written with selects instead of a branch per stage: the lanes of a pass are spread over
@@ -470,7 +472,7 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
             }
             // ---- (2) walk to the next draw ----
             while (req == 0 && mode == M_ADV) {
-                if (a.dbg && lane == (__ffs(__activemask()) - 1))
+                if (TRACE && a.dbg && lane == (__ffs(__activemask()) - 1))
                     ++c_adv_trips;
                 if (in_capture) {
                     // capture step (:412-423): one Poisson draw per non-zero bin
@@ -540,7 +542,7 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
 #ifndef SONICS_NO_RECONVERGE
             __syncwarp(m_adv); // lanes leave the walk loop at different trips: classify / set up together
 #endif
-            if (TRACE && req != 0) {
+            if (TRACE && a.trace && req != 0) {
                 if (tr_n < a.trace_cap) {
                     SonicsTraceEntry e;
                     e.kind = req;
@@ -577,7 +579,7 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
         }
         if (__all_sync(SONICS_FULL, mode == M_EXIT))
             break;
-        if (a.dbg) {
+        if (TRACE && a.dbg) {
             ++c_pass;
 #pragma unroll
             for (int mm = 0; mm < 7; ++mm)
@@ -632,7 +634,7 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
         {
             const unsigned m_full = __ballot_sync(SONICS_FULL, mode == M_FULL);
             if (__popc(m_full) >= SONICS_THR_FULL || (m_full != 0u && m_busy == 0u)) {
-                if (a.dbg) {
+                if (TRACE && a.dbg) {
                     ++c_full_runs;
                     c_full_lanes += __popc(m_full);
                 }
@@ -649,7 +651,7 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
         }
     }
 
-    if (a.dbg) {
+    if (TRACE && a.dbg) {
         for (int o = 16; o > 0; o >>= 1)
             c_adv_trips += __shfl_down_sync(SONICS_FULL, c_adv_trips, o);
         if (lane == 0) {

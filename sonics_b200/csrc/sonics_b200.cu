@@ -315,7 +315,7 @@ static int launch_simulate(sonics_ctx *ctx, SimArgs &a, const TableInfo &ti, boo
     a.trace = ctx->trace;
     a.trace_len = ctx->trace_len;
     a.trace_cap = ctx->trace_cap;
-    auto pcr = ctx->trace ? k_pcr<true> : k_pcr<false>;
+    auto pcr = (ctx->trace || ctx->dbg) ? k_pcr<true> : k_pcr<false>;
     if (!dev_scratch || scratch_bytes < scratch_bytes_for(32, a.Wcap))
         return fail(SONICS_ERR_SPACE, "simulation scratch of %zu bytes is below the minimum %zu", scratch_bytes,
                     scratch_bytes_for(32, a.Wcap));

@@ -103,3 +103,27 @@ def test_replay_noise_and_wide_window():
 def test_replay_option_matrix(kw):
     n, dp, dlam, kinds = replay_all([CFG1, "8|50;9|3;14|20", "2|9;3|1"], [0.0, 0.004, 0.0], 64, seed=11, **kw)
     assert n > 0 and dlam == 0.0 and dp < 1e-4, (n, dp, dlam)
+
+
+def test_counters_and_trace_hooks_are_independent():
+    """Both hooks select the instrumented kernel; either may be on without the other, and results match the
+    production instantiation bit for bit."""
+    import torch
+    e = engine()
+    params = eng.make_params()
+    table = e.build_table_from_arrays(params, [orc.parse_reads(CFG1)], [0.0])
+    ref = e.simulate(params, table, 256, seed=3)
+    e.sync()
+    counters = torch.zeros(16, dtype=torch.int64, device="cuda:0")
+    from sonics_b200._abi import check
+    check(e.lib.sonics_debug_counters(e.ctx, counters.data_ptr()))
+    try:
+        got = e.simulate(params, table, 256, seed=3)
+        e.sync()
+    finally:
+        check(e.lib.sonics_debug_counters(e.ctx, None))
+    assert (got["lnL"] == ref["lnL"]).all() and (got["group"] == ref["group"]).all()
+    c = counters.cpu().numpy()
+    assert c[0] > 0 and c[12] > 0  # passes, warps
+    out, trace, tlen, pools = e.simulate_traced(params, table, 256, 3, trace_cap=4096)
+    assert (out["lnL"][0] == ref["lnL"][0].cpu().numpy()).all() and (tlen > 0).all()
