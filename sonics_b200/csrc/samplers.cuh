@@ -65,19 +65,21 @@ __device__ __forceinline__ void inv_setup(DrawState &v, int n, float p)
     v.fk = 0.0f;
 }
 __device__ __forceinline__ void inv_start(DrawState &v, uint32_t bits) { v.fk = u01_fine(bits); }
-// up to max_steps steps of the sequential search; true when the draw is finished (result v.ix)
-__device__ __forceinline__ bool inv_run(DrawState &v, const float *rcp_tab, int max_steps)
+// the sequential search, to its end (at most icap < SONICS_RCP_TABLE steps; n*p < 10 makes ~2 typical):
+// result v.ix.  No step counter and a running table pointer: the loop runs with ~3 lanes, so every
+// instruction in it is paid ten times over.
+__device__ __forceinline__ void inv_run(DrawState &v, const float *rcp_tab)
 {
-    int k = 0;
-    while (v.fk > v.A && v.ix < v.icap && k < max_steps) {
-        ++v.ix;
-        ++k;
-        v.fk -= v.A;
-        v.A *= fmaf(v.a, rcp_tab[v.ix], -v.b);
+    const float *r = rcp_tab + v.ix;
+    const float *const rend = rcp_tab + v.icap;
+    float u = v.fk, px = v.A;
+    while (u > px && r < rend) {
+        ++r;
+        u -= px;
+        px *= fmaf(v.a, *r, -v.b);
     }
-    return !(v.fk > v.A && v.ix < v.icap);
+    v.ix = (int)(r - rcp_tab);
 }
-
 // ---- BTRS: Binomial(n, p), p <= 0.5, n*p >= 10 ----
 __device__ __forceinline__ void btrs_setup(DrawState &s, int n, float p)
 {
@@ -163,8 +165,7 @@ __device__ __forceinline__ int binomial(Rng &rng, int n, float p, uint32_t bits_
     if ((float)n * pp < 10.0f) {
         inv_setup(s, n, pp);
         inv_start(s, bits_a);
-        while (!inv_run(s, rcp_tab, 1 << 20))
-            ;
+        inv_run(s, rcp_tab);
         k = s.ix;
     } else {
         btrs_setup(s, n, pp);

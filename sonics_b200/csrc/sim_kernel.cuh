@@ -211,7 +211,7 @@ __device__ __forceinline__ size_t pool_index(int u, int Wcap, int bin)
     return ((size_t)(u >> 5) * Wcap + bin) * 32 + (u & 31);
 }
 
-enum { M_ADV = 0, M_BTRS = 1, M_INV0 = 2, M_BOUND = 3, M_FULL = 4, M_POIS = 5, M_EXIT = 6, M_INVRUN = 7 };
+enum { M_ADV = 0, M_BTRS = 1, M_INV0 = 2, M_BOUND = 3, M_FULL = 4, M_POIS = 5, M_EXIT = 6 };
 enum { PC_NEWSIM = 0, PC_RESULT = 1, PC_CAPRESULT = 2, PC_SCAN = 3 };
 // deferral thresholds: a minority phase runs when this many lanes wait for it (or nothing else can progress)
 #ifndef SONICS_THR_BOUND
@@ -222,9 +222,6 @@ enum { PC_NEWSIM = 0, PC_RESULT = 1, PC_CAPRESULT = 2, PC_SCAN = 3 };
 #endif
 #ifndef SONICS_THR_FULL
 #define SONICS_THR_FULL 4
-#endif
-#ifndef SONICS_INV_CHUNK
-#define SONICS_INV_CHUNK 32 // sequential-search steps per pass (a bound, rarely reached: n*p < 10)
 #endif
 #ifndef SONICS_PCR_MIN_BLOCKS
 #define SONICS_PCR_MIN_BLOCKS 7 // x 128 threads x 72 registers; 8 x 64 spills 80 B per thread and is 1.6 % slower
@@ -583,33 +580,28 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
             ++c_pass;
 #pragma unroll
             for (int mm = 0; mm < 7; ++mm)
-                c_mode[mm] += __popc(__ballot_sync(SONICS_FULL, mode == mm || (mm == M_INV0 && mode == M_INVRUN)));
+                c_mode[mm] += __popc(__ballot_sync(SONICS_FULL, mode == mm));
         }
         const unsigned m_busy = __ballot_sync(SONICS_FULL, mode == M_ADV || mode == M_BTRS || mode == M_POIS);
 
         // ================= INV (deferred) + one rejection step: shared random-word fetch =================
-        // Small-mean binomials are drawn by inversion when enough lanes wait for it (set-up, then
-        // bounded chunks of the sequential search: stragglers continue in the next INV run together
-        // with the newcomers).  Lanes in a rejection sampler run ONE trial per pass (an immediate
+        // Small-mean binomials are drawn by inversion when enough lanes wait for it (set-up and the whole
+        // sequential search in that pass: a pass costs a waiting lane more than the search's tail).  Lanes in a rejection sampler run ONE trial per pass (an immediate
         // retry would execute with ~1 lane).  Every lane that consumes randomness in this pass takes
         // the next 64-bit block of ITS OWN simulation's stream -- the block counter advances only
         // when the simulation consumes, never with the warp's pass count -- through one call site.
         {
-            const unsigned m_inv = __ballot_sync(SONICS_FULL, mode == M_INV0 || mode == M_INVRUN);
+            const unsigned m_inv = __ballot_sync(SONICS_FULL, mode == M_INV0);
             const bool run_inv = __popc(m_inv) >= SONICS_THR_INV || (m_inv != 0u && m_busy == 0u);
             uint2 words = make_uint2(0u, 0u);
             if (mode == M_BTRS || mode == M_POIS || (run_inv && mode == M_INV0))
                 words = rng.pair();
-            if (run_inv && (mode == M_INV0 || mode == M_INVRUN)) {
-                if (mode == M_INV0) {
-                    inv_setup(ds, dn, ds.p);
-                    inv_start(ds, words.x);
-                    mode = M_INVRUN;
-                }
-                if (inv_run(ds, rcp_tab, SONICS_INV_CHUNK)) {
-                    x = flip ? dn - ds.ix : ds.ix;
-                    mode = M_ADV;
-                }
+            if (run_inv && mode == M_INV0) {
+                inv_setup(ds, dn, ds.p);
+                inv_start(ds, words.x);
+                inv_run(ds, rcp_tab);
+                x = flip ? dn - ds.ix : ds.ix;
+                mode = M_ADV;
             } else if (mode == M_BTRS) {
                 const int r = btrs_trial(ds, words.x, words.y);
                 if (r == 1) {
