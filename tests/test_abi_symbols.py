@@ -60,3 +60,14 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".inl", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower().replace("no oracle", ""), os.path.join(dirpath, f)
+
+
+def test_tools_and_cli_do_not_use_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/: the measurement tools
+    and the CLI must not."""
+    import re
+    for d in ("tools", "bin"):
+        for f in os.listdir(os.path.join(ROOT, d)):
+            text = open(os.path.join(ROOT, d, f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), os.path.join(d, f)
+            assert "libsonics_oracle" not in text and "oracle/_ref" not in text, os.path.join(d, f)

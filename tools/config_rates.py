@@ -12,20 +12,27 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-from oracle import oracle as orc  # noqa: E402  (parse_reads / auto_noise_coef only: input preparation)
-from sonics_b200 import engine as eng  # noqa: E402
-from tests.util import CFG1, CFG2, CFG3  # noqa: E402
+import math  # noqa: E402
+
+from sonics_b200 import driver, engine as eng  # noqa: E402
+
+CFG1 = "8|5;9|113;10|89"
+CFG2 = "5|1;6|1;7|5;8|11;9|20;10|24;11|2;12|1"
+CFG3 = ";".join(
+    "%d|%d" % (a, int(5 + 400 * math.exp(-0.5 * ((a - 28) / 6) ** 2) + 300 * math.exp(-0.5 * ((a - 36) / 5) ** 2)))
+    for a in range(10, 50))
 
 
 def main():
     e = eng.Engine(0)
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 2000000
-    cases = [("cfg1", CFG1, 0.0, {}), ("cfg2", CFG2, 0.0, {}),
-             ("cfg3", CFG3, None, dict(n_cycles=30, capture_cycle=16))]
-    for name, spec, nc, kw in cases:
-        reads = orc.parse_reads(spec)
-        if nc is None:
-            nc = float(np.float32(orc.auto_noise_coef(reads)))
+    cases = [("cfg1", CFG1, {}), ("cfg2", CFG2, {}), ("cfg3", CFG3, dict(n_cycles=30, capture_cycle=16))]
+    for name, spec, kw in cases:
+        # the CLI's own pre-filter: alleles + automatic noise coefficient (sonics:407-416)
+        kind, (reads, nc) = driver.prefilter(("sample", "Block", ".", spec),
+                                             {"one_allele_threshold": 45, "noise_threshold": 0.05},
+                                             {"monte_carlo": True})
+        nc = float(np.float32(nc))
         params = eng.make_params(**kw)
         table = e.build_table_from_arrays(params, [reads], [nc])
         out = e.simulate(params, table, n, seed=1)
