@@ -70,15 +70,19 @@ __device__ __forceinline__ void inv_start(DrawState &v, uint32_t bits) { v.fk = 
 // instruction in it is paid ten times over.
 __device__ __forceinline__ void inv_run(DrawState &v, const float *rcp_tab)
 {
-    const float *r = rcp_tab + v.ix;
-    const float *const rend = rcp_tab + v.icap;
+    // 32-bit shared-memory addresses: a generic float* costs two extra 64-bit adds per step
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(rcp_tab);
+    uint32_t r = base + 4u * (uint32_t)v.ix;
+    const uint32_t rend = base + 4u * (uint32_t)v.icap;
     float u = v.fk, px = v.A;
     while (u > px && r < rend) {
-        ++r;
+        r += 4u;
         u -= px;
-        px *= fmaf(v.a, *r, -v.b);
+        float rc;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(rc) : "r"(r));
+        px *= fmaf(v.a, rc, -v.b);
     }
-    v.ix = (int)(r - rcp_tab);
+    v.ix = (int)((r - base) >> 2);
 }
 // ---- BTRS: Binomial(n, p), p <= 0.5, n*p >= 10 ----
 __device__ __forceinline__ void btrs_setup(DrawState &s, int n, float p)
