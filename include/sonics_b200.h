@@ -251,8 +251,11 @@ int sonics_debug_sample(sonics_ctx *ctx, int kind, int n, double p, int64_t coun
  * its single parse and per-row append, sonics:246-343,436, would bound 8 GPUs): sonics_vcf_parse_range
  * parses the data lines whose first byte lies in [byte_begin, byte_end) (byte_end < 0: end of file; header
  * lines are read by every range), so ranges that tile the file parse every line exactly once, in order;
- * sonics_rows_write_part writes one range's rows with or without the header line; sonics_rows_concat joins
- * the parts in rank order and removes them.  The random choice of --strict 0 is keyed by (seed, line
+ * sonics_rows_write_part writes one range's rows (flags: 1 = header line first, 2 = append to the file);
+ * sonics_rows_concat joins the parts in rank order and removes them.  sonics_vcf_uids gives every genotype
+ * to simulate its RNG key = its cell in the (data line x sample) grid of the whole file, from the number of
+ * data lines before the range (sonics_vcf_lines_before, a newline scan; sonics_vcf_count(4) of the ranges
+ * before it gives the same number), so results do not depend on how the file is cut.  The random choice of --strict 0 is keyed by (seed, line
  * offset) and does not depend on the tiling. */
 typedef struct sonics_vcf sonics_vcf;
 int sonics_vcf_parse(const char *path, int strict, int one_allele_threshold, double noise_threshold, int monte_carlo,
@@ -264,12 +267,14 @@ void sonics_vcf_free(sonics_vcf *vcf);
 int64_t sonics_vcf_count(const sonics_vcf *vcf, int what);
 int sonics_vcf_fill(const sonics_vcf *vcf, int32_t *allele_off, int32_t *allele, int32_t *reads, float *noise_coef,
                     int32_t *row_kind);
+int sonics_vcf_uids(const sonics_vcf *vcf, int64_t line_base, uint32_t *uid_out);
+int sonics_vcf_lines_before(const char *path, int64_t byte_end, int64_t *n_lines);
 const char *sonics_vcf_warning(const sonics_vcf *vcf, int64_t i);
 int sonics_rows_write(const char *path, const sonics_vcf *vcf, const SonicsVerdict *verdicts, int64_t n_verdicts,
                       int monte_carlo, const char *add_ratios, const char *name, const char *block);
 int sonics_rows_write_part(const char *path, const sonics_vcf *vcf, const SonicsVerdict *verdicts,
                            int64_t n_verdicts, int monte_carlo, const char *add_ratios, const char *name,
-                           const char *block, int with_header);
+                           const char *block, int flags);
 int sonics_rows_concat(const char *path, const char *const *parts, int n_parts);
 
 /* Kernel launches issued by this ctx so far (bench.py's gpu_launches). */

@@ -102,6 +102,8 @@ PROTOTYPES = {
     "sonics_vcf_free": (None, [_P]),
     "sonics_vcf_count": (_I64, [_P, _I]),
     "sonics_vcf_fill": (_I, [_P, _P, _P, _P, _P, _P]),
+    "sonics_vcf_uids": (_I, [_P, _I64, _P]),
+    "sonics_vcf_lines_before": (_I, [ctypes.c_char_p, _I64, ctypes.POINTER(_I64)]),
     "sonics_vcf_warning": (ctypes.c_char_p, [_P, _I64]),
     "sonics_rows_write": (_I, [ctypes.c_char_p, _P, _P, _I64, _I, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]),
     "sonics_rows_write_part": (_I, [ctypes.c_char_p, _P, _P, _I64, _I, ctypes.c_char_p, ctypes.c_char_p,

@@ -467,6 +467,66 @@ int64_t sonics_vcf_count(const sonics_vcf *v, int what)
     return 0;
 }
 
+/* RNG keys of the genotypes to simulate, in CSR order: (line_base + data-line ordinal within this range) *
+ * samples + sample index -- the genotype's cell in the (data line x sample) grid of the whole file, so the key
+ * does not depend on how the file is cut into ranges. */
+int sonics_vcf_uids(const sonics_vcf *v, int64_t line_base, uint32_t *uid_out)
+{
+    if (!v || !uid_out || line_base < 0)
+        return fail(SONICS_ERR_ARG, "sonics_vcf_uids: bad argument");
+    const int64_t ns = (int64_t)v->samples.size();
+    size_t j = 0;
+    for (size_t r = 0; r < v->row_kind.size(); ++r)
+        if (v->row_kind[r] == 2) {
+            const int64_t cell = (line_base + v->row_block[r]) * ns + v->row_sample[r];
+            if (cell > 0xFFFFFFFFll)
+                return fail(SONICS_ERR_RANGE, "more than 2^32 (line, sample) cells in the VCF");
+            uid_out[j++] = (uint32_t)cell;
+        }
+    return SONICS_OK;
+}
+
+/* Number of data lines (not '#', not empty) whose first byte lies before byte_end (< 0: whole file): the
+ * line_base of a range that starts at byte_end. */
+int sonics_vcf_lines_before(const char *path, int64_t byte_end, int64_t *n_lines)
+{
+    if (!path || !n_lines)
+        return fail(SONICS_ERR_ARG, "sonics_vcf_lines_before: NULL argument");
+    FILE *fp = fopen(path, "rb");
+    if (!fp)
+        return fail(SONICS_ERR_ARG, "sonics_vcf_lines_before: cannot open %s", path);
+    std::vector<char> buf(4 << 20);
+    int64_t pos = 0, count = 0;
+    bool at_start = true, pending_cr = false; // pending_cr: the line so far is a lone '\r'
+    size_t n;
+    while ((byte_end < 0 || pos < byte_end) && (n = fread(buf.data(), 1, buf.size(), fp)) > 0) {
+        for (size_t i = 0; i < n && (byte_end < 0 || pos < byte_end); ++i, ++pos) {
+            const char c = buf[i];
+            if (at_start) {
+                at_start = false;
+                if (c == '\n') {
+                    at_start = true;
+                } else if (c == '\r') {
+                    pending_cr = true;
+                } else if (c != '#') {
+                    ++count;
+                }
+            } else if (pending_cr) {
+                pending_cr = false;
+                if (c == '\n')
+                    at_start = true; // "\r\n": an empty line
+                else
+                    ++count; // a line that begins with '\r' and goes on (malformed; the parser will report it)
+            } else if (c == '\n') {
+                at_start = true;
+            }
+        }
+    }
+    fclose(fp);
+    *n_lines = count;
+    return SONICS_OK;
+}
+
 /* Copies the CSR of the genotypes to simulate (sizes from sonics_vcf_count) and the per-row kinds. */
 int sonics_vcf_fill(const sonics_vcf *v, int32_t *allele_off, int32_t *allele, int32_t *reads, float *noise_coef,
                     int32_t *row_kind)
@@ -504,12 +564,12 @@ int sonics_rows_write_part(const char *path, const sonics_vcf *vcf, const Sonics
         add_perc = split(add_ratios, ';');
     std::string out;
     out.reserve(1 << 20);
-    if (with_header)
+    if (with_header & 1)
         out += monte_carlo ? "sample\tblock\tref\tgenotype\tidentity\tidentity_75th_percentile\tr_squared\t"
                          "r_squared_75th_percentile\tlnL\tlnL_75th_percentile\trepeats\n"
                        : "sample\tblock\tref\tgenotype\tidentity\tr_squared\tlnL\tfilter\tMWUtes_pval\tbest_lnL_ratio\t"
                          "quartile_lnL_ratio\trepeats\tadditional_ratios\n";
-    FILE *fp = fopen(path, "w");
+    FILE *fp = fopen(path, (with_header & 2) ? "a" : "w");
     if (!fp)
         return fail(SONICS_ERR_ARG, "sonics_rows_write: cannot open %s", path);
     if (!vcf) {

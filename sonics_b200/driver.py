@@ -220,20 +220,21 @@ def shard_bounds(n, world, rank):
 
 
 def run_batch_verdicts(allele_off, allele, reads, noise, constants, ranges, options, seed, device=0, chunk=65536,
-                       uid_offset=0):
-    """Verdict array for a CSR batch of genotypes (chunked); uid = global position keys the RNG."""
+                       uids=None):
+    """Verdict array for a CSR batch of genotypes (device batches of `chunk`); uids key the RNG per genotype
+    (default: the position in this batch)."""
     from . import engine as eng
     e = sonics_mod.engine(device)
     params = eng.params_from_dicts(constants, ranges, options)
     n = len(noise)
+    uids = np.arange(n, dtype=np.uint32) if uids is None else np.ascontiguousarray(uids, dtype=np.uint32)
     parts = []
     for c0 in range(0, n, chunk):
         c1 = min(n, c0 + chunk)
         off = allele_off[c0:c1 + 1] - allele_off[c0]
         a0, a1 = allele_off[c0], allele_off[c1]
-        uids = np.arange(uid_offset + c0, uid_offset + c1, dtype=np.uint32)
         parts.append(e.genotype_batch(params, off, allele[a0:a1], reads[a0:a1], noise[c0:c1], options["repetitions"],
-                                      seed, uid=uids))
+                                      seed, uid=uids[c0:c1]))
     return np.concatenate(parts) if parts else np.zeros(0, dtype=eng.VERDICT_DTYPE)
 
 
@@ -243,8 +244,72 @@ def _csr_slice(allele_off, allele, reads, noise, lo, hi):
 
 
 def _verdict_shard_worker(args):
-    off, al, rd, nz, constants, ranges, options, seed, device, chunk, lo = args
-    return run_batch_verdicts(off, al, rd, nz, constants, ranges, options, seed, device, chunk, uid_offset=lo)
+    off, al, rd, nz, constants, ranges, options, seed, device, chunk, uids = args
+    return run_batch_verdicts(off, al, rd, nz, constants, ranges, options, seed, device, chunk, uids)
+
+
+PIECE_BYTES = 8 << 20  # VCF bytes per pipeline piece (~140 k genotypes of a 32-sample lobSTR file)
+
+
+def vcf_pipeline(feed_in, byte_range, line_base, out_path, header, constants, options, seed, compute,
+                 piece_bytes=None):
+    """One process's share of VCF mode, pipelined: the file range is cut into pieces; while the GPU runs
+    piece k (`compute`, a blocking native call that releases the GIL), one host thread parses piece k+1
+    (sonics_vcf_parse_range) and another appends the rows of piece k-1 to out_path (sonics_rows_write_part).
+
+    A genotype's RNG key is its cell in the (data line x sample) grid of the whole file: line_base = data
+    lines before byte_range (hostio.lines_before), then every piece adds the lines it parsed -- so neither
+    the pieces nor the ranks change the output.  Returns (rows, simulated genotypes, timings dict)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from . import hostio
+    lo, hi = byte_range
+    end = os.path.getsize(feed_in) if hi < 0 else hi
+    # pieces small enough that the un-overlapped first parse and last write are a small share of the range
+    piece_bytes = piece_bytes or max(1 << 20, min(PIECE_BYTES, (end - lo) // 8))
+    cuts = list(range(lo, end, piece_bytes)) + [end]
+    pieces = [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1)]
+    if pieces and hi < 0:
+        pieces[-1] = (pieces[-1][0], -1)
+    tm = {"ingest": 0.0, "simulate": 0.0, "write": 0.0, "pieces": len(pieces)}
+    n_rows = n_sim = 0
+
+    def parse(rng):
+        t = time.time()
+        v = hostio.Vcf(feed_in, options["strict"], constants["one_allele_threshold"], constants["noise_threshold"],
+                       options["monte_carlo"], seed, byte_range=rng)
+        return v, time.time() - t
+
+    def write(v, verdicts, first):
+        t = time.time()
+        hostio.write_rows(out_path, verdicts, v, options["monte_carlo"], options["add_ratios"], options["name"],
+                          options["block"], header=header and first, append=not first)
+        v.close()
+        return time.time() - t
+
+    if not pieces:
+        hostio.write_rows(out_path, np.zeros(0, dtype=hostio.VERDICT_DTYPE), None, options["monte_carlo"],
+                          options["add_ratios"], options["name"], options["block"], header=header)
+        return 0, 0, tm
+    with ThreadPoolExecutor(1) as parser, ThreadPoolExecutor(1) as writer:
+        nxt = parser.submit(parse, pieces[0])
+        pending = None
+        for k in range(len(pieces)):
+            v, tp = nxt.result()
+            tm["ingest"] += tp
+            if k + 1 < len(pieces):
+                nxt = parser.submit(parse, pieces[k + 1])
+            uids = v.uids(line_base)
+            line_base += v.n_blocks
+            n_rows += v.n_rows
+            n_sim += v.n_sim
+            t = time.time()
+            verdicts = compute(v.allele_off, v.allele, v.reads, v.noise_coef, uids)
+            tm["simulate"] += time.time() - t
+            if pending is not None:
+                tm["write"] += pending.result()
+            pending = writer.submit(write, v, verdicts, k == 0)
+        tm["write"] += pending.result()
+    return n_rows, n_sim, tm
 
 
 def run_sonics(feed_in, constants, ranges, options, seed=None, gpus=1, chunk=65536):
@@ -265,14 +330,24 @@ def run_sonics(feed_in, constants, ranges, options, seed=None, gpus=1, chunk=655
         return _run_sonics_per_genotype(feed_in, constants, ranges, options, seed, out_file_path)
     if options["vcf_mode"] and world > 1:
         return _run_vcf_ranks(feed_in, constants, ranges, options, seed, chunk, out_file_path, rank, world)
+    if options["vcf_mode"] and gpus <= 1:
+        t0 = time.time()
+        n_rows, n_sim, tm = vcf_pipeline(
+            feed_in, (0, -1), 0, out_file_path, True, constants, options, seed,
+            lambda off, al, rd, nz, uids: run_batch_verdicts(off, al, rd, nz, constants, ranges, options, seed, 0,
+                                                             chunk, uids))
+        LAST_TIMINGS.clear()
+        LAST_TIMINGS.update(tm, join=0.0, genotypes=n_sim, wall=time.time() - t0)
+        if n_rows == 0:
+            raise Exception("No valid genotype after parsing VCF file.")
+        return
     vcf = None
-    t0 = time.time()
-    if options["vcf_mode"]:
+    if options["vcf_mode"]:  # --gpus N in one process: parse once, contiguous shards to N worker processes
         vcf = hostio.Vcf(feed_in, options["strict"], constants["one_allele_threshold"], constants["noise_threshold"],
                          options["monte_carlo"], seed)
         if vcf.n_rows == 0:
             raise Exception("No valid genotype after parsing VCF file.")
-        off, al, rd, nz = vcf.allele_off, vcf.allele, vcf.reads, vcf.noise_coef
+        off, al, rd, nz, uids = vcf.allele_off, vcf.allele, vcf.reads, vcf.noise_coef, vcf.uids(0)
     else:
         if rank != 0:
             return
@@ -289,32 +364,30 @@ def run_sonics(feed_in, constants, ranges, options, seed=None, gpus=1, chunk=655
         from . import engine as eng
         off, al, rd = eng.to_csr([payload[0]])
         nz = np.array([payload[1]], dtype=np.float32)
+        uids = np.zeros(1, dtype=np.uint32)
     n = len(nz)
-    t1 = time.time()
     if gpus > 1:
         import multiprocessing as mp
         jobs = []
         for r in range(gpus):
             lo, hi = shard_bounds(n, gpus, r)
-            jobs.append(_csr_slice(off, al, rd, nz, lo, hi) + (constants, ranges, options, seed, r, chunk, lo))
+            jobs.append(_csr_slice(off, al, rd, nz, lo, hi) + (constants, ranges, options, seed, r, chunk, uids[lo:hi]))
         with mp.get_context("spawn").Pool(gpus) as pool:
             verdicts = np.concatenate(pool.map(_verdict_shard_worker, jobs))
     else:
-        verdicts = run_batch_verdicts(off, al, rd, nz, constants, ranges, options, seed, 0, chunk)
-    t2 = time.time()
+        verdicts = run_batch_verdicts(off, al, rd, nz, constants, ranges, options, seed, 0, chunk, uids)
     hostio.write_rows(out_file_path, verdicts, vcf, options["monte_carlo"], options["add_ratios"], options["name"],
                       options["block"])
-    LAST_TIMINGS.update(ingest=t1 - t0, simulate=t2 - t1, write=time.time() - t2, join=0.0, genotypes=int(n))
 
 
-def _run_vcf_ranks(feed_in, constants, ranges, options, seed, chunk, out_file_path, rank, world, compute=None):
+def _run_vcf_ranks(feed_in, constants, ranges, options, seed, chunk, out_file_path, rank, world, compute=None,
+                   piece_bytes=None):
     """VCF mode under torchrun, one process per GPU: the ranks share ingest, simulation and output.
 
-    Rank r parses the data lines that start in its byte range of the file (hostio.byte_ranges), learns the
-    number of genotypes before its range from one all_gather of counts (the RNG is keyed by the genotype's
-    position in the whole file, so the rows do not depend on the number of ranks), runs its genotypes on
-    its GPU, and writes its rows to <out>.part<r>; rank 0 joins the parts in rank order.  No collective
-    touches the data path.  `compute` replaces the GPU call in the CPU (gloo) test of this plumbing."""
+    Rank r runs vcf_pipeline() on its byte range of the file (hostio.byte_ranges; the number of data lines
+    before the range comes from a newline scan, so no rank waits for another) and writes <out>.part<r>; at the
+    end one all_gather of part sizes gives every rank its offset in the output file and each rank copies its
+    own part there.  No collective touches the data path.  `compute` replaces the GPU call in the CPU (gloo) test."""
     import torch.distributed as dist
     from . import hostio
     if not dist.is_initialized():
@@ -326,27 +399,35 @@ def _run_vcf_ranks(feed_in, constants, ranges, options, seed, chunk, out_file_pa
         else:
             dist.init_process_group("gloo")
     t0 = time.time()
-    vcf = hostio.Vcf(feed_in, options["strict"], constants["one_allele_threshold"], constants["noise_threshold"],
-                     options["monte_carlo"], seed, byte_range=hostio.byte_ranges(feed_in, world)[rank])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    compute = compute or (lambda off, al, rd, nz, uids: run_batch_verdicts(
+        off, al, rd, nz, constants, ranges, options, seed, local, chunk, uids))
+    rng = hostio.byte_ranges(feed_in, world)[rank]
+    line_base = hostio.lines_before(feed_in, rng[0]) if rng[0] > 0 else 0
+    n_rows, n_sim, tm = vcf_pipeline(feed_in, rng, line_base, "%s.part%d" % (out_file_path, rank), rank == 0,
+                                     constants, options, seed, compute, piece_bytes)
     t1 = time.time()
+    # join: every rank copies its own part to its offset of the output file (parallel; rank 0 sizes the file)
+    part = "%s.part%d" % (out_file_path, rank)
     counts = [None] * world
-    dist.all_gather_object(counts, (vcf.n_rows, vcf.n_sim))
+    dist.all_gather_object(counts, (n_rows, os.path.getsize(part)))
+    if rank == 0:
+        with open(out_file_path, "wb") as f:
+            f.truncate(sum(c[1] for c in counts))
+    dist.barrier()
+    with open(out_file_path, "r+b") as fo, open(part, "rb") as fi:
+        fo.seek(sum(c[1] for c in counts[:rank]))
+        while True:
+            buf = fi.read(8 << 20)
+            if not buf:
+                break
+            fo.write(buf)
+    os.unlink(part)
+    dist.barrier()
+    LAST_TIMINGS.clear()
+    LAST_TIMINGS.update(tm, join=time.time() - t1, genotypes=n_sim, wall=time.time() - t0)
     if sum(c[0] for c in counts) == 0:
         raise Exception("No valid genotype after parsing VCF file.")
-    uid0 = sum(c[1] for c in counts[:rank])
-    local = int(os.environ.get("LOCAL_RANK", rank))
-    compute = compute or (lambda off, al, rd, nz, uid_offset: run_batch_verdicts(
-        off, al, rd, nz, constants, ranges, options, seed, local, chunk, uid_offset))
-    t2 = time.time()
-    verdicts = compute(vcf.allele_off, vcf.allele, vcf.reads, vcf.noise_coef, uid0)
-    t3 = time.time()
-    hostio.write_rows("%s.part%d" % (out_file_path, rank), verdicts, vcf, options["monte_carlo"],
-                      options["add_ratios"], options["name"], options["block"], header=(rank == 0))
-    t4 = time.time()
-    dist.barrier()
-    if rank == 0:
-        hostio.concat_parts(out_file_path, ["%s.part%d" % (out_file_path, r) for r in range(world)])
-    LAST_TIMINGS.update(ingest=t1 - t0, simulate=t3 - t2, write=t4 - t3, join=time.time() - t4, genotypes=int(vcf.n_sim))
 
 
 def _run_sonics_per_genotype(feed_in, constants, ranges, options, seed, out_file_path):

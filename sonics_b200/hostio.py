@@ -37,6 +37,13 @@ class Vcf:
         for w in self.warnings[:20]:
             logging.warning(w)
 
+    def uids(self, line_base=0):
+        """RNG keys of the genotypes to simulate: (line_base + data-line ordinal) * samples + sample index, with
+        line_base = the number of data lines before this range (lines_before)."""
+        out = np.zeros(self.n_sim, dtype=np.uint32)
+        check(self.lib.sonics_vcf_uids(self.handle, int(line_base), out.ctypes.data))
+        return out
+
     def close(self):
         if self.handle:
             self.lib.sonics_vcf_free(self.handle)
@@ -49,14 +56,23 @@ class Vcf:
             pass
 
 
-def write_rows(path, verdicts, vcf=None, monte_carlo=False, add_ratios="", name="sample", block="Block", header=True):
+def lines_before(path, byte_end):
+    """Data lines of the VCF that start before byte_end (the line_base of a range starting there)."""
+    n = ctypes.c_int64(0)
+    check(_abi.load().sonics_vcf_lines_before(str(path).encode(), int(byte_end), ctypes.byref(n)))
+    return n.value
+
+
+def write_rows(path, verdicts, vcf=None, monte_carlo=False, add_ratios="", name="sample", block="Block", header=True,
+               append=False):
     """Header + rows of run_sonics() (sonics:174-207, :437); verdicts: structured array (VERDICT_DTYPE).
-    header=False writes the rows only (a part of a multi-rank run, see concat_parts)."""
+    header=False writes the rows only, append=True adds them to an existing file (pieces of a pipelined or
+    multi-rank run, see concat_parts)."""
     lib = _abi.load()
     v = np.ascontiguousarray(verdicts, dtype=VERDICT_DTYPE)
     check(lib.sonics_rows_write_part(str(path).encode(), vcf.handle if vcf is not None else None, v.ctypes.data,
                                      len(v), int(bool(monte_carlo)), add_ratios.encode(), name.encode(),
-                                     block.encode(), int(bool(header))))
+                                     block.encode(), int(bool(header)) | (2 if append else 0)))
 
 
 def byte_ranges(path, world):

@@ -122,27 +122,72 @@ WORKER = textwrap.dedent("""
     vcf_path, out_path = sys.argv[1], sys.argv[2]
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    def compute(off, al, rd, nz, uid0):   # stands in for the GPU: a verdict that encodes (uid, first allele, reads)
+    def compute(off, al, rd, nz, uids):   # stands in for the GPU: a verdict that encodes (uid, first allele, reads)
         v = np.zeros(len(nz), dtype=hostio.VERDICT_DTYPE)
-        v["allele_lo"] = al[off[:-1]]
-        v["allele_hi"] = al[off[1:] - 1]
-        v["filter"] = 1
-        v["run_reps"] = uid0 + np.arange(len(nz))
-        v["lnL"] = -np.add.reduceat(rd, off[:-1]).astype(np.float64) if len(nz) else 0
+        if len(nz):
+            v["allele_lo"] = al[off[:-1]]
+            v["allele_hi"] = al[off[1:] - 1]
+            v["filter"] = 1
+            v["run_reps"] = uids
+            v["lnL"] = -np.add.reduceat(rd, off[:-1]).astype(np.float64)
         return v
     constants = {"one_allele_threshold": 45, "noise_threshold": 0.05}
     options = {"strict": 1, "monte_carlo": False, "add_ratios": "", "name": "sample", "block": "Block"}
-    driver._run_vcf_ranks(vcf_path, constants, None, options, 5, 65536, out_path, rank, world, compute=compute)
+    driver._run_vcf_ranks(vcf_path, constants, None, options, 5, 65536, out_path, rank, world, compute=compute,
+                          piece_bytes=700)   # several pipeline pieces per rank
     dist.barrier()
     if rank == 0:
+        assert driver.LAST_TIMINGS["pieces"] > 2
         whole = hostio.Vcf(vcf_path)
-        hostio.write_rows(out_path + ".single", compute(whole.allele_off, whole.allele, whole.reads, whole.noise_coef, 0),
-                          whole)
+        hostio.write_rows(out_path + ".single",
+                          compute(whole.allele_off, whole.allele, whole.reads, whole.noise_coef, whole.uids(0)), whole)
         assert open(out_path).read() == open(out_path + ".single").read()
         assert not os.path.exists(out_path + ".part0") and not os.path.exists(out_path + ".part1")
         print("RANKS_OK", whole.n_sim)
     dist.destroy_process_group()
 """)
+
+
+def _stub_compute(off, al, rd, nz, uids):
+    from sonics_b200 import hostio
+    v = np.zeros(len(nz), dtype=hostio.VERDICT_DTYPE)
+    if len(nz):
+        v["allele_lo"] = al[off[:-1]]
+        v["allele_hi"] = al[off[1:] - 1]
+        v["filter"] = 1
+        v["run_reps"] = uids
+        v["lnL"] = -np.add.reduceat(rd, off[:-1]).astype(np.float64)
+    return v
+
+
+@pytest.mark.parametrize("piece_bytes", [64, 333, 5000, 1 << 20])
+def test_pipelined_vcf_pieces_reproduce_the_whole_file_run(tmp_path, piece_bytes):
+    """Single-process VCF mode is a pipeline over byte pieces of the file (parse k+1 / simulate k / write k-1):
+    the output and the RNG keys (cell in the line x sample grid) do not depend on the piece size."""
+    from sonics_b200 import hostio
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import synth_vcf
+    vcf = str(tmp_path / "in.vcf")
+    synth_vcf.write_vcf(vcf, synth_vcf.make_genotypes(31, 4, seed=8, cov=(20, 300), noisy=0.3), 4)
+    constants = {"one_allele_threshold": 45, "noise_threshold": 0.05}
+    options = {"strict": 1, "monte_carlo": False, "add_ratios": "", "name": "sample", "block": "Block"}
+    whole = hostio.Vcf(vcf)
+    uids = whole.uids(0)
+    assert len(set(uids.tolist())) == whole.n_sim and (np.diff(uids.astype(np.int64)) > 0).all()
+    assert hostio.lines_before(vcf, -1) == whole.n_blocks == 31
+    hostio.write_rows(str(tmp_path / "whole.txt"),
+                      _stub_compute(whole.allele_off, whole.allele, whole.reads, whole.noise_coef, uids), whole)
+    out = str(tmp_path / "piped.txt")
+    n_rows, n_sim, tm = driver.vcf_pipeline(vcf, (0, -1), 0, out, True, constants, options, 5, _stub_compute,
+                                            piece_bytes=piece_bytes)
+    assert (n_rows, n_sim) == (whole.n_rows, whole.n_sim)
+    assert open(out).read() == open(tmp_path / "whole.txt").read()
+    # a range in the middle of the file with its line_base from the newline scan
+    size = os.path.getsize(vcf)
+    lo = size // 3
+    base = hostio.lines_before(vcf, lo)
+    mid = hostio.Vcf(vcf, byte_range=(lo, -1))
+    assert list(mid.uids(base)) == list(uids[whole.n_sim - mid.n_sim:])
 
 
 def test_two_rank_gloo_vcf_ingest_simulate_write(tmp_path):

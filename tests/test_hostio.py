@@ -171,6 +171,10 @@ def test_byte_range_tilings_parse_every_line_once(tmp_path, strict):
         a = hostio.Vcf(p, strict, seed=77, byte_range=(0, c))
         b = hostio.Vcf(p, strict, seed=77, byte_range=(c, -1))
         assert _join([_csr(a), _csr(b)]) == ref, c
+        # the newline scan counts exactly the data lines the parser assigns to [0, c) ...
+        assert hostio.lines_before(p, c) == a.n_blocks, c
+        # ... so the RNG keys (cells of the line x sample grid) of a range do not depend on the cut
+        assert list(a.uids(0)) + list(b.uids(a.n_blocks)) == list(whole.uids(0)), c
     for world in (3, 4, 8, 64):
         parts = [_csr(hostio.Vcf(p, strict, seed=77, byte_range=r)) for r in hostio.byte_ranges(p, world)]
         assert _join(parts) == ref, world
