@@ -536,9 +536,7 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
                 }
             }
             // ---- (3) classify the draw ----
-#ifndef SONICS_NO_RECONVERGE
-            __syncwarp(m_adv); // lanes leave the walk loop at different trips: classify / set up together
-#endif
+            __syncwarp(m_adv); // lanes leave the walk loop at different trips: classify / set up together (+8 %)
             if (TRACE && a.trace && req != 0) {
                 if (tr_n < a.trace_cap) {
                     SonicsTraceEntry e;
