@@ -148,8 +148,9 @@ int sonics_table_max_window(sonics_ctx *ctx);
  *   dev_identity (fp64), dev_rsq (fp32; a C float in the reference, sonics.pyx:300): descriptors of
  *                                 the simulated sequencing readout, sonics.pyx:341-357,365-384
  *   dev_simpar [4*o .. 4*o+3]   fp64 down, up, capture, efficiency (the report columns :387-393).
- * The RNG is Philox4x32-10 keyed by (seed; uid, j): results do not depend on
- * launch geometry, on sim_begin/sim_count splits, or on the GPU that runs them. */
+ * The RNG is counter-based (Philox4x32-10 for priors / start alleles / readout, Philox2x32-10 for the draws
+ * of the PCR cycles), keyed by (seed; uid, j): results do not depend on launch geometry, on
+ * sim_begin/sim_count splits, or on the GPU that runs them. */
 int sonics_simulate(sonics_ctx *ctx, const SonicsParams *params, const void *dev_table, int n_gt,
                     const int32_t *dev_active, int n_active, int64_t sim_begin, int64_t sim_count, uint64_t seed,
                     int64_t out_stride, int64_t out_offset, double *dev_lnL, uint16_t *dev_group,
