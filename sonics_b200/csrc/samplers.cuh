@@ -27,10 +27,33 @@ namespace sonics {
 
 #define SONICS_RCP_TABLE 192 // 1/x for x in [0, 192) (inversion recurrences; index 0 unused)
 
+// Single-instruction MUFU approximations.  __fdividef / __logf / sqrtf wrap the same units in range scaling
+// for denormal and huge operands (5-8 instructions each; the BTRS quick path is ~17 instructions long and
+// contains one reciprocal).  Every operand here is a probability, a count below 2^31 or a uniform
+// >= 2^-24, far from both ends of the range; the accuracy class is the same (<= 2 ulp).
+__device__ __forceinline__ float rcp_fast(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float log_fast(float x)
+{
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r * 0.69314718056f;
+}
+__device__ __forceinline__ float sqrt_fast(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // Stirling tail fc(k) = ln k! - [ (k+1/2) ln(k+1) - (k+1) + 1/2 ln(2 pi) ]
 __device__ __forceinline__ float stirling_tail(float k)
 {
-    const float r = __fdividef(1.0f, k + 1.0f);
+    const float r = rcp_fast(k + 1.0f);
     const float r2 = r * r;
     return r * (0.083333333333f - r2 * (0.002777777778f - r2 * 0.000793650794f));
 }
@@ -57,7 +80,7 @@ struct DrawState {
 __device__ __forceinline__ void inv_setup(DrawState &v, int n, float p)
 {
     const float q = 1.0f - p;
-    v.b = __fdividef(p, q);
+    v.b = p * rcp_fast(q);
     v.a = (float)(n + 1) * v.b;
     v.A = __expf((float)n * log1pf(-p)); // px = q^n
     v.icap = n < SONICS_RCP_TABLE - 1 ? n : SONICS_RCP_TABLE - 1; // P(X > 160 | np < 10) < 1e-130
@@ -94,9 +117,9 @@ __device__ __forceinline__ void btrs_setup(DrawState &s, int n, float p)
     const float hi = s.fn * p;
     const float lo = fmaf(s.fn, p, -hi);
     s.npq = hi * q;
-    const float spq = sqrtf(s.npq);
+    const float spq = sqrt_fast(s.npq);
     s.b = 1.15f + 2.53f * spq;
-    const float rb = __fdividef(1.0f, s.b);
+    const float rb = rcp_fast(s.b);
     s.a = -0.0873f + 0.0248f * s.b + 0.01f * p;
     s.vr = 0.92f - 4.2f * rb;
     s.alpha = (2.83f + 5.1f * rb) * spq;
@@ -112,19 +135,19 @@ __device__ __forceinline__ int btrs_trial(DrawState &s, uint32_t bits_a, uint32_
     const float u = u01_open(bits_a) - 0.5f;
     const float v = u01_open(bits_b);
     const float us = 0.5f - fabsf(u);
-    const float rus = __fdividef(1.0f, us);
+    const float rus = rcp_fast(us);
     // k = floor((2a/us + b) u + c); the fractional work stays below 2^22 in magnitude
     s.fk = s.ci + floor_small(fmaf(fmaf(2.0f * s.a, rus, s.b), u, s.cf));
     if (us >= 0.07f && v <= s.vr)
         return 1; // quick accept
     if (!(s.fk >= 0.0f && s.fk <= s.fn))
         return 0;
-    s.A = __logf(v * s.alpha * __fdividef(1.0f, fmaf(s.a * rus, rus, s.b)));
+    s.A = log_fast(v * s.alpha * rcp_fast(fmaf(s.a * rus, rus, s.b)));
     const float d = s.fk - s.fm;
     const float ad = fabsf(d);
     if (ad < 0.5f * s.npq - 1.0f) {
         // BTPE step 5.2: t - rho <= ln f(k)/f(m) <= t + rho
-        const float rn = __fdividef(1.0f, s.npq);
+        const float rn = rcp_fast(s.npq);
         const float t = -0.5f * d * d * rn;
         const float rho = (ad * rn) * (fmaf(ad, fmaf(ad, 0.33333333f, 0.625f), 0.16666667f) * rn + 0.5f);
         const float eps = 1e-5f * (1.0f + fabsf(t)); // margin for the fp32 evaluation of A, t and rho
@@ -142,7 +165,7 @@ __device__ __forceinline__ int btrs_trial(DrawState &s, uint32_t bits_a, uint32_
 __device__ __forceinline__ bool btrs_full(const DrawState &s)
 {
     const float q = 1.0f - s.p;
-    const float r = __fdividef(s.p, q);
+    const float r = s.p * rcp_fast(q);
     const float d = s.fk - s.fm;
     const float nk = s.fn - s.fk + 1.0f;
     const float k1 = s.fk + 1.0f;
@@ -200,7 +223,7 @@ __device__ __forceinline__ int poisson_small(float lam, uint32_t bits)
     while (u > px && x < 200) {
         ++x;
         u -= px;
-        px *= __fdividef(lam, (float)x);
+        px *= lam * rcp_fast((float)x);
     }
     return x;
 }
@@ -209,11 +232,11 @@ __device__ __forceinline__ int poisson_small(float lam, uint32_t bits)
 __device__ __forceinline__ void pois_setup(DrawState &s, float lam) // lam >= 10
 {
     s.fn = lam;
-    const float slam = sqrtf(lam);
+    const float slam = sqrt_fast(lam);
     s.b = 0.931f + 2.53f * slam;
     s.a = -0.059f + 0.02483f * s.b;
-    s.alpha = 1.1239f + __fdividef(1.1328f, s.b - 3.4f); // 1 / alpha
-    s.vr = 0.9277f - __fdividef(3.6224f, s.b - 2.0f);
+    s.alpha = fmaf(1.1328f, rcp_fast(s.b - 3.4f), 1.1239f); // 1 / alpha
+    s.vr = fmaf(-3.6224f, rcp_fast(s.b - 2.0f), 0.9277f);
     s.ci = floorf(lam);
     s.cf = (lam - s.ci) + 0.43f;
     s.ix = 0;
@@ -225,21 +248,21 @@ __device__ __forceinline__ bool pois_trial(DrawState &s, uint32_t bits_a, uint32
     const float u = u01_open(bits_a) - 0.5f;
     const float v = u01_open(bits_b);
     const float us = 0.5f - fabsf(u);
-    const float rus = __fdividef(1.0f, us);
+    const float rus = rcp_fast(us);
     const float fk = s.ci + floor_small(fmaf(fmaf(2.0f * s.a, rus, s.b), u, s.cf));
     s.ix = (int)fk;
     if (us >= 0.07f && v <= s.vr)
         return true;
     if (fk < 0.0f || (us < 0.013f && v > us))
         return false;
-    const float lhs = __logf(v * s.alpha * __fdividef(1.0f, fmaf(s.a * rus, rus, s.b)));
+    const float lhs = log_fast(v * s.alpha * rcp_fast(fmaf(s.a * rus, rus, s.b)));
     float rhs;
     if (fk >= 10.0f) {
-        const float rk = __fdividef(1.0f, fk);
+        const float rk = rcp_fast(fk);
         const float y = (s.fn - fk) * rk;
-        rhs = fk * (log1pf(y) - y) - 0.5f * __logf(6.2831853f * fk) - rk * (0.083333333f - 0.0027777778f * rk * rk);
+        rhs = fk * (log1pf(y) - y) - 0.5f * log_fast(6.2831853f * fk) - rk * (0.083333333f - 0.0027777778f * rk * rk);
     } else {
-        rhs = -s.fn + fk * __logf(s.fn) - lgammaf(fk + 1.0f);
+        rhs = -s.fn + fk * log_fast(s.fn) - lgammaf(fk + 1.0f);
     }
     return lhs <= rhs;
 }

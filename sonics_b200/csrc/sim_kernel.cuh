@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
                         ct = cur;
                         const float prob_up = -E_up, prob_down = -E_dn;
                         p_slip = fmaf(-prob_up, prob_down, prob_up + prob_down); // 1-(1-pd)(1-pu)
-                        p_upn = __fdividef(prob_up, prob_up + prob_down);
+                        p_upn = prob_up * rcp_fast(prob_up + prob_down);
                     }
                     n_stage = stutter ? 3 : 1;
                     stage = 0;
