@@ -169,9 +169,10 @@ __device__ __forceinline__ bool btrs_full(const DrawState &s)
     const float d = s.fk - s.fm;
     const float nk = s.fn - s.fk + 1.0f;
     const float k1 = s.fk + 1.0f;
-    const float t1 = (s.fm + 0.5f) * log1pf(-d / k1);
-    const float t2 = (s.fn - s.fm + 0.5f) * log1pf(d / nk);
-    const float t3 = d * logf(r * nk / k1);
+    const float rk1 = rcp_fast(k1), rnk = rcp_fast(nk); // IEEE divisions cost ~10 instructions each here
+    const float t1 = (s.fm + 0.5f) * log1pf(-d * rk1);
+    const float t2 = (s.fn - s.fm + 0.5f) * log1pf(d * rnk);
+    const float t3 = d * logf(r * nk * rk1);
     const float h = t1 + t2 + t3 + stirling_tail(s.fm) + stirling_tail(s.fn - s.fm) - stirling_tail(s.fk) -
                     stirling_tail(s.fn - s.fk);
     return s.A <= h;

@@ -303,7 +303,9 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
                             u = (int)t;
                             tr_n = 0;
                             const int64_t gu = a.unit_base + u;
-                            const int slot = (int)(gu / a.sims_per_gt);
+                            // 32-bit division when it fits (the 64-bit one is a ~100-instruction call)
+                            const int slot = gu < 0x7fffffffLL ? (int)((uint32_t)gu / (uint32_t)a.sims_per_gt)
+                                                               : (int)(gu / a.sims_per_gt);
                             const int jrel = (int)(gu - (int64_t)slot * a.sims_per_gt);
                             const int g = a.active ? a.active[slot] : slot;
                             const GtHeader h = a.t.hdr[g];
