@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
     int cycle = 1;
     int ct = 0; // function-scope `ct` of the reference; goes stale below the floor (:478)
     int b = 1, bend = 0, prev = 0, cur = 0, carry = 0;
-    int stage = 0, n_stage = 1, amp = 0, slip = 0;
+    int stage = 0, n_stage = 1;
     float p_slip = 0.0f, p_upn = 0.0f, E_up = 0.0f, E_dn = 0.0f;
     int x = 0;         // result of the draw that just finished
     int dn = 0;        // n of the draw in flight
@@ -435,17 +435,18 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
             // Written with selects instead of a branch per stage: the lanes of a pass are spread over
             // the three stages, and a 3-way branch would run each third separately.
             if (pc == PC_RESULT) {
-                amp = stage == 0 ? x : amp;
-                slip = stage == 1 ? x : slip;
+                // mol_amp joins the bin as soon as it is known (stage 0), mol_slip leaves it (stage 1) and waits
+                // in `carry` -- zero for the duration of a visit -- for the third draw: no per-draw state beyond
+                // what the sweep carries anyway (products[al] += mol_amp - mol_slip, :466)
+                cur += stage == 0 ? x : (stage == 1 ? -x : 0);
+                carry = stage == 1 ? x : carry;
                 // the bin is finished after the third draw, after a draw that returned 0 (nothing
                 // amplified / nothing slipped), or after the single draw of a below-floor bin (:477-479)
                 const bool bin_done = stage == 2 || x == 0 || n_stage == 1;
                 if (bin_done) {
-                    const int slip_e = stage >= 1 ? slip : 0;
                     const int up_e = stage == 2 ? x : 0;
-                    const int down = slip_e - up_e; // mol_down = mol_slip - mol_up
-                    cur += amp - slip_e;
-                    carry = down > 0 ? up_e : 0; // sic: up-stutter only lands when mol_down > 0 (:473-476)
+                    const int down = carry - up_e; // mol_down = mol_slip - mol_up
+                    carry = down > 0 ? up_e : 0;   // sic: up-stutter only lands when mol_down > 0 (:473-476)
                     if (b > 0)
                         hist[(b - 1) * 32] = prev + down;
                     if (down > 0 && b - 1 < live_lo)
