@@ -199,8 +199,12 @@ def test_two_rank_gloo_vcf_ingest_simulate_write(tmp_path):
     synth_vcf.write_vcf(vcf, synth_vcf.make_genotypes(23, 3, seed=4, cov=(20, 300), noisy=0.3), 3)
     worker = str(tmp_path / "worker.py")
     open(worker, "w").write(WORKER % ROOT)
+    import socket
+    with socket.socket() as sk:  # a free rendezvous port (a fixed one may be taken on a shared box)
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29631", worker, vcf,
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), worker, vcf,
                           str(tmp_path / "out.txt")], capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "RANKS_OK" in out.stdout
