@@ -19,7 +19,6 @@ import argparse
 import logging
 import os
 import re
-import sys
 import time
 
 import numpy as np
