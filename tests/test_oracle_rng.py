@@ -3,7 +3,6 @@ poisson, uniform, randint/choice) bit for bit against golden vectors produced by
 numpy.random itself (tests/golden/make_golden.py::gen_rng).  These are the
 third-party primitives behind sonics.pyx:37-43,321,324,354,368,420,428,450-462,478."""
 import numpy as np
-import pytest
 
 from oracle import oracle as orc
 from tests.util import load
