@@ -237,9 +237,24 @@ def gen_vcf():
     with tempfile.NamedTemporaryFile("w", suffix=".vcf", delete=False) as f:
         f.write(VCF_TEXT)
         path = f.name
-    out = {"vcf": VCF_TEXT, "strict1": [list(map(lambda x: int(x) if isinstance(x, (int, np.integer)) else x, t))
-                                        for t in cli.parse_vcf(path, 1)]}
+    clean = lambda rows: [list(map(lambda x: int(x) if isinstance(x, (int, np.integer)) else x, t)) for t in rows]
+    out = {"vcf": VCF_TEXT, "strict1": clean(cli.parse_vcf(path, 1))}
     os.unlink(path)
+    # odd-but-valid random files (tests/util.random_vcf, regenerated from the seed at test time)
+    import hashlib
+    import logging
+    from tests.util import random_vcf
+    logging.disable(logging.WARNING)
+    out["random"] = []
+    for seed in range(8):
+        rs = np.random.RandomState(1000 + seed)
+        text = random_vcf(rs, 40, int(rs.randint(1, 6)))
+        with tempfile.NamedTemporaryFile("w", suffix=".vcf", delete=False) as f:
+            f.write(text)
+        out["random"].append({"seed": 1000 + seed, "sha256": hashlib.sha256(text.encode()).hexdigest(),
+                              "strict1": clean(cli.parse_vcf(f.name, 1))})
+        os.unlink(f.name)
+    logging.disable(logging.NOTSET)
     return out
 
 

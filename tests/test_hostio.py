@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from sonics_b200 import driver, engine as eng, hostio, sonics as drop_in
-from tests.util import load
+from tests.util import load, random_vcf
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -205,3 +205,18 @@ def test_part_files_concatenate_to_the_whole_output(tmp_path):
     hostio.concat_parts(str(tmp_path / "joined.txt"), parts)
     assert open(tmp_path / "joined.txt").read() == open(tmp_path / "whole.txt").read()
     assert not any(os.path.exists(q) for q in parts)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_native_vcf_ingest_random_differential(tmp_path, seed):
+    """Randomised differential test against the Python mirror of parse_vcf() + the pre-filters (--strict 1)."""
+    rs = np.random.RandomState(1000 + seed)
+    p = str(tmp_path / "r.vcf")
+    open(p, "w").write(random_vcf(rs, 40, int(rs.randint(1, 6))))
+    parsed, kinds, off, al, rd, nz = _python_path(p, 1)
+    v = hostio.Vcf(p, 1)
+    assert v.n_rows == len(parsed)
+    assert list(v.row_kind) == [{"skip": 0, "row": 1, "sim": 2}[k[0]] for k in kinds]
+    assert (v.allele_off == off).all() and (v.allele == al).all() and (v.reads == rd).all()
+    assert (v.noise_coef == nz).all()
+    assert {0, 2} <= set(v.row_kind.tolist())
