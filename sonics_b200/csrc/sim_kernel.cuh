@@ -21,25 +21,27 @@
 // so a cycle costs one LDS + one STS per live bin on top of the samplers.
 //
 // Control flow.  Simulations differ in how many draws they need (second start allele, efficiency,
-// stutter rates) and every draw in how many rejection trials / inversion steps it takes; ~2 % of
-// the binomial trials need the expensive Stirling test.  Lockstep formulations measured 7 of 32
+// stutter rates) and every draw in how many rejection trials / inversion steps it takes; ~15 % of
+// the BTRS draws need the expensive Stirling test (a quarter of them have n*p < 100).  Lockstep formulations measured 7 of 32
 // lanes active (ncu, profiles/r01_k1_v2_ncu.txt) and a warp-per-batch state machine still had 12.5
 // lanes idle waiting for the slowest simulation of the warp.  Therefore:
 //   * lanes are PERSISTENT: a lane that finishes a simulation stores its pool and immediately pulls
 //     the next work unit (genotype, simulation index) from a global counter -- lanes of one warp
 //     work on different simulations, possibly of different genotypes, at different cycles;
 //   * each lane runs its simulation as a small state machine and the warp iterates over "passes";
-//     in one pass a lane performs at most one of
+//     in one pass a lane performs ADVANCE when its draw has finished and then at most one of
 //       ADVANCE  consume the finished draw, walk the sweep to the next draw, set it up
-//       INV      up to 8 steps of sequential-search inversion        (n*min(p,q) < 10)
-//       BTRS     one or two transformed-rejection trials incl. squeeze (otherwise)
-//       POIS     one or two PTRS trials (capture step)
+//       INV      set-up + the whole sequential-search inversion      (n*min(p,q) < 10) -- run when
+//                >= 6 lanes wait for it
+//       BTRS     one transformed-rejection trial incl. squeeze        (otherwise)
+//       POIS     one PTRS trial / the small-lambda inversion          (capture step)
 //       FULL     the Stirling test of an undecided BTRS candidate -- run only when >= 4 lanes wait
-//                for it (or nothing else can progress), so the long path executes with several lanes;
+//                for it (or nothing else can progress), so the long path executes with several lanes
+//       BOUNDARY end of sweep / end of simulation + next work unit / capture set-up (>= 4 lanes);
 //   * the lnL (25 fp64 Lanczos evaluations) is not done by the finishing lane -- that would run at
 //     1/32 occupancy -- but by K1b, one lane per simulation, fully convergent.
 // Nothing in a simulation's stream depends on neighbouring lanes: random words come from the
-// simulation's own Philox counter, which advances only when that simulation consumes a block, so
+// simulation's own Philox counters (rng.cuh), which advance only when that simulation consumes a block, so
 // results are independent of launch geometry and any simulation can be replayed bit for bit.
 // Reference quirks reproduced: the stale `ct` of the below-floor branch (:478),
 // the count/index mix in cap_set (:414), fp32 efficiency/capture/hit (:401),
