@@ -242,6 +242,15 @@ def _csr_slice(allele_off, allele, reads, noise, lo, hi):
     return allele_off[lo:hi + 1] - a0, allele[a0:a1], reads[a0:a1], noise[lo:hi]
 
 
+def shard_jobs(off, al, rd, nz, uids, gpus, common, chunk):
+    """Argument tuples of _verdict_shard_worker: contiguous CSR shards, one per GPU, each with its own RNG keys."""
+    jobs = []
+    for r in range(gpus):
+        lo, hi = shard_bounds(len(nz), gpus, r)
+        jobs.append(_csr_slice(off, al, rd, nz, lo, hi) + common + (r, chunk, uids[lo:hi]))
+    return jobs
+
+
 def _verdict_shard_worker(args):
     off, al, rd, nz, constants, ranges, options, seed, device, chunk, uids = args
     return run_batch_verdicts(off, al, rd, nz, constants, ranges, options, seed, device, chunk, uids)
@@ -367,10 +376,7 @@ def run_sonics(feed_in, constants, ranges, options, seed=None, gpus=1, chunk=655
     n = len(nz)
     if gpus > 1:
         import multiprocessing as mp
-        jobs = []
-        for r in range(gpus):
-            lo, hi = shard_bounds(n, gpus, r)
-            jobs.append(_csr_slice(off, al, rd, nz, lo, hi) + (constants, ranges, options, seed, r, chunk, uids[lo:hi]))
+        jobs = shard_jobs(off, al, rd, nz, uids, gpus, (constants, ranges, options, seed), chunk)
         with mp.get_context("spawn").Pool(gpus) as pool:
             verdicts = np.concatenate(pool.map(_verdict_shard_worker, jobs))
     else:

@@ -226,3 +226,22 @@ def test_two_rank_gloo_vcf_ingest_simulate_write(tmp_path):
                           str(tmp_path / "out.txt")], capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "RANKS_OK" in out.stdout
+
+
+def test_shard_jobs_cover_the_batch_with_their_own_keys():
+    """--gpus N in one process: contiguous CSR shards whose concatenation is the batch, RNG keys sliced alike."""
+    off = np.array([0, 2, 5, 7, 9, 12, 14, 16, 19, 21, 23, 25], dtype=np.int32)   # 11 ragged genotypes
+    al = np.arange(25, dtype=np.int32)
+    rd = al + 1
+    nz = np.linspace(0, 1, 11).astype(np.float32)
+    uids = (np.arange(11) * 7 + 3).astype(np.uint32)
+    for gpus in (2, 3, 4, 11, 16):
+        jobs = driver.shard_jobs(off, al, rd, nz, uids, gpus, ("c", "r", "o", 5), 65536)
+        assert len(jobs) == gpus and [j[8] for j in jobs] == list(range(gpus))
+        got_al = np.concatenate([j[1] for j in jobs])
+        got_uid = np.concatenate([j[10] for j in jobs])
+        got_first = [int(j[1][j[0][k]]) for j in jobs for k in range(len(j[3]))]
+        assert (got_al == al).all() and (got_uid == uids).all()
+        assert got_first == [int(al[off[g]]) for g in range(11)]
+        assert all(j[0][0] == 0 and j[0][-1] == len(j[1]) == len(j[2]) for j in jobs)
+        assert [j[4:8] for j in jobs] == [("c", "r", "o", 5)] * gpus and all(j[9] == 65536 for j in jobs)
