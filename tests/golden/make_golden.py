@@ -258,6 +258,46 @@ def gen_vcf():
     return out
 
 
+def gen_prefilter():
+    """process_one_genotype() of the reference CLI (sonics:345-439) with monte_carlo() stubbed out: what it
+    writes for 0- / 1-allele genotypes and which alleles / noise_coef it hands to the simulation."""
+    import importlib.machinery
+    import logging
+    import tempfile
+    from tests.util import random_vcf
+    cli = importlib.machinery.SourceFileLoader("sonics_cli_ref2", "/root/reference/sonics").load_module()
+
+    def stub(reps, constants, ranges, options):
+        al = constants["alleles"]
+        return "STUB\t%r\t%s" % (float(constants["noise_coef"]),
+                                  ";".join("%d|%d" % (a, al[a]) for a in np.nonzero(al)[0]))
+    cli.sonics.monte_carlo = stub
+    logging.disable(logging.WARNING)
+    tuples = [("s", "b", 10, g) for g in
+              ["9|46", "9|45", "9|44", "9|0", "", "0|5;9|100", "8|5;9|113;10|89", "5|1;6|1;7|5;8|11;9|20;10|24;11|2;12|1",
+               "8|1;9|1000", "8|2;9|1000;10|30", "3|1;4|1;5|1;6|1;7|1;8|1;9|1;10|1;11|1;12|1;13|1;14|1;15|1;16|1;17|1;18|1;19|1;20|1;21|1;22|1;23|1;24|900",
+               "9|7;9|300;10|5", "-3|5;9|50;10|40"]]
+    for seed in (1000, 1001):
+        rs = np.random.RandomState(seed)
+        text = random_vcf(rs, 40, int(rs.randint(1, 6)))
+        with tempfile.NamedTemporaryFile("w", suffix=".vcf", delete=False) as f:
+            f.write(text)
+        tuples += [tuple(int(x) if isinstance(x, (int, np.integer)) else x for x in t) for t in cli.parse_vcf(f.name, 1)]
+        os.unlink(f.name)
+    cases = []
+    for mc in (False, True):
+        for t in tuples:
+            with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
+                out_path = f.name
+            constants = {"one_allele_threshold": 45, "noise_threshold": 0.05}
+            options = {"out_file_path": out_path, "monte_carlo": mc, "repetitions": 1000}
+            cli.process_one_genotype(t, constants, None, options)
+            cases.append({"tuple": list(t), "mc": mc, "written": open(out_path).read()})
+            os.unlink(out_path)
+    logging.disable(logging.NOTSET)
+    return {"cases": cases}
+
+
 def dump(name, obj):
     with open(os.path.join(HERE, name), "w") as f:
         json.dump(obj, f, indent=0, separators=(",", ":"))
@@ -266,7 +306,9 @@ def dump(name, obj):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["rng", "one_repeat", "monte_carlo", "lnl", "vcf"]
+    which = sys.argv[1:] or ["rng", "one_repeat", "monte_carlo", "lnl", "vcf", "prefilter"]
+    if "prefilter" in which:
+        dump("prefilter.json", gen_prefilter())
     if "vcf" in which:
         dump("vcf_parse.json", gen_vcf())
     if "rng" in which:

@@ -245,3 +245,31 @@ def test_shard_jobs_cover_the_batch_with_their_own_keys():
         assert got_first == [int(al[off[g]]) for g in range(11)]
         assert all(j[0][0] == 0 and j[0][-1] == len(j[1]) == len(j[2]) for j in jobs)
         assert [j[4:8] for j in jobs] == [("c", "r", "o", 5)] * gpus and all(j[9] == 65536 for j in jobs)
+
+
+def _expected_written(t, kind, payload):
+    if kind == "skip":
+        return ""
+    if kind == "row":
+        return "{}\t{}\t{}\t{}\n".format(t[0], t[1], t[2], payload)
+    alleles, noise_coef = payload
+    return "{}\t{}\t{}\tSTUB\t{!r}\t{}\n".format(
+        t[0], t[1], t[2], float(noise_coef), ";".join("%d|%d" % (a, alleles[a]) for a in np.nonzero(alleles)[0]))
+
+
+def test_prefilter_matches_reference_process_one_genotype():
+    """Golden: the reference's process_one_genotype() with monte_carlo() stubbed (tests/golden/make_golden.py) --
+    what is written for 0-/1-allele genotypes (incl. the MC-mode row that is built but never written) and the
+    alleles / auto-noise coefficient handed to the simulation, on hand-made and random genotypes."""
+    import logging
+    logging.disable(logging.WARNING)
+    try:
+        cases = load("prefilter.json")["cases"]
+        assert len(cases) > 400
+        for c in cases:
+            t = tuple(c["tuple"])
+            kind, payload = driver.prefilter(t, {"one_allele_threshold": 45, "noise_threshold": 0.05},
+                                             {"monte_carlo": c["mc"]})
+            assert _expected_written(t, kind, payload) == c["written"], c
+    finally:
+        logging.disable(logging.NOTSET)

@@ -220,3 +220,32 @@ def test_native_vcf_ingest_random_differential(tmp_path, seed):
     assert (v.allele_off == off).all() and (v.allele == al).all() and (v.reads == rd).all()
     assert (v.noise_coef == nz).all()
     assert {0, 2} <= set(v.row_kind.tolist())
+
+
+def test_native_prefilters_match_reference_golden(tmp_path):
+    """The native ingest's row kinds and noise coefficients on the random files of the golden fixture equal what the
+    reference's process_one_genotype() does with the same genotypes (tests/golden/prefilter.json)."""
+    import logging
+    cases = load("prefilter.json")["cases"]
+    logging.disable(logging.WARNING)
+    try:
+        for mc in (False, True):
+            want = {tuple(c["tuple"]): c["written"] for c in cases if c["mc"] == mc}
+            for seed in (1000, 1001):
+                rs = np.random.RandomState(seed)
+                p = str(tmp_path / ("r%d.vcf" % seed))
+                open(p, "w").write(random_vcf(rs, 40, int(rs.randint(1, 6))))
+                parsed = driver.parse_vcf(p, 1)
+                v = hostio.Vcf(p, 1, monte_carlo=mc)
+                assert v.n_rows == len(parsed)
+                j = 0
+                for t, kind in zip(parsed, v.row_kind):
+                    w = want[tuple(t)]
+                    assert kind == (0 if w == "" else 2 if "STUB" in w else 1), (t, w)
+                    if kind == 2:
+                        ref_nc = float(w.split("\t")[4])
+                        assert v.noise_coef[j] == np.float32(ref_nc), (t, w)
+                        j += 1
+                assert j == v.n_sim
+    finally:
+        logging.disable(logging.NOTSET)
