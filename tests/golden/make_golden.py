@@ -294,8 +294,23 @@ def gen_prefilter():
             cli.process_one_genotype(t, constants, None, options)
             cases.append({"tuple": list(t), "mc": mc, "written": open(out_path).read()})
             os.unlink(out_path)
+    # whole files through run_sonics(): header, row order, name / block / ref columns, no_simulations rows
+    files = []
+    texts = [VCF_TEXT]
+    rs = np.random.RandomState(1002)
+    texts.append(random_vcf(rs, 40, int(rs.randint(2, 6))))
+    for text in texts:
+        for mc in (False, True):
+            d = tempfile.mkdtemp()
+            vcf = os.path.join(d, "in.vcf")
+            open(vcf, "w").write(text)
+            constants = {"one_allele_threshold": 45, "noise_threshold": 0.05}
+            options = {"out_path": d, "file_name": "out.txt", "monte_carlo": mc, "vcf_mode": True, "strict": 1,
+                       "processes": 0, "repetitions": 1000, "name": "sample", "block": "Block"}
+            cli.run_sonics(vcf, constants, None, options)
+            files.append({"vcf": text, "mc": mc, "out": open(os.path.join(d, "out.txt")).read()})
     logging.disable(logging.NOTSET)
-    return {"cases": cases}
+    return {"cases": cases, "files": files}
 
 
 def dump(name, obj):

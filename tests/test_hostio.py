@@ -249,3 +249,28 @@ def test_native_prefilters_match_reference_golden(tmp_path):
                 assert j == v.n_sim
     finally:
         logging.disable(logging.NOTSET)
+
+
+def test_native_output_file_structure_matches_reference_run_sonics(tmp_path):
+    """Golden: whole output files of the reference's run_sonics() with monte_carlo() stubbed.  The native path
+    (ingest -> verdicts -> row writer) must produce the same header, the same rows in the same order with the same
+    sample / block / ref columns and the same no_simulations rows; simulated rows are compared up to their payload."""
+    import logging
+    logging.disable(logging.WARNING)
+    try:
+        for k, f in enumerate(load("prefilter.json")["files"]):
+            p = str(tmp_path / ("in%d.vcf" % k))
+            open(p, "w").write(f["vcf"])
+            v = hostio.Vcf(p, 1, monte_carlo=f["mc"])
+            verdicts = np.zeros(v.n_sim, dtype=hostio.VERDICT_DTYPE)
+            verdicts["allele_lo"], verdicts["allele_hi"], verdicts["filter"], verdicts["run_reps"] = 9, 10, 1, 100
+            out = str(tmp_path / ("out%d.txt" % k))
+            hostio.write_rows(out, verdicts, v, monte_carlo=f["mc"])
+
+            def mask(text):
+                lines = text.split("\n")
+                return [lines[0]] + [ln if "no_simulations" in ln else "\t".join(ln.split("\t")[:3]) for ln in lines[1:]]
+            assert mask(open(out).read()) == mask(f["out"]), (k, f["mc"])
+            assert sum("no_simulations" in ln for ln in f["out"].split("\n")) == int((v.row_kind == 1).sum())
+    finally:
+        logging.disable(logging.NOTSET)
