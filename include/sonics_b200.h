@@ -134,6 +134,9 @@ int sonics_table_build(sonics_ctx *ctx, const SonicsParams *params, int n_gt, co
                        void *dev_table, size_t dev_table_bytes, void *stream);
 /* Largest live window (histogram bins) over the table: sizes shared memory. */
 int sonics_table_max_window(sonics_ctx *ctx);
+/* Forget a table built into dev_table (the ctx keeps a small host-side record per table; call this before the
+ * buffer is freed or reused for something else).  Unknown pointers are ignored. */
+int sonics_table_release(sonics_ctx *ctx, const void *dev_table);
 
 /* ---- K1: fixed-count simulations (one_repeat() x sim_count per genotype) --
  * For every genotype g listed in dev_active (all n_gt when dev_active is NULL)
@@ -156,11 +159,28 @@ int sonics_simulate(sonics_ctx *ctx, const SonicsParams *params, const void *dev
                     int64_t out_stride, int64_t out_offset, double *dev_lnL, uint16_t *dev_group,
                     double *dev_identity, float *dev_rsq, double *dev_simpar, void *dev_scratch,
                     size_t dev_scratch_bytes, void *stream);
-/* Scratch for sonics_simulate / sonics_replay_best: the final PCR pools of the work units of one chunk
- * (K1a -> K1b hand-off).  sonics_scratch_bytes(n_units, max_window) is the size that runs
- * n_units = n_active * sim_count in a single chunk; anything from sonics_scratch_bytes(32, max_window)
- * up works (more chunks, two launches each). */
+/* K1 exists in two forms that run the same simulations -- same draws in the same order from the same Philox
+ * streams, bit-identical results (tests/test_gpu_lockstep.py):
+ *   SONICS_KERNEL_LOCKSTEP    sort the work units by (genotype, start alleles, quantised priors), then 32 similar
+ *                             simulations per warp in lockstep, lnL / readout fused (sim_lockstep.cuh);
+ *   SONICS_KERNEL_PERSISTENT  one lane = one simulation at a time as a state machine + a separate lnL kernel
+ *                             (sim_kernel.cuh); the draw trace and the control-flow counters live here.
+ * SONICS_KERNEL_AUTO (default) = lockstep unless a trace / counter buffer is attached.  The environment variable
+ * SONICS_K1=persistent|lockstep sets the initial value of a new ctx (measurement switch). */
+enum { SONICS_KERNEL_AUTO = 0, SONICS_KERNEL_PERSISTENT = 1, SONICS_KERNEL_LOCKSTEP = 2 };
+int sonics_set_kernel(sonics_ctx *ctx, int kernel);
+/* Lockstep form: bits of the sort key spent on the quantised efficiency / down / up priors (each <= 15; eff_bits
+ * < 0 = automatic: about log2(simulations per start-allele group / 32) bits, half of them on the efficiency).  The
+ * sort only decides which lane runs which simulation: results never depend on it (tuning knob; env
+ * SONICS_SORT_BITS=e,d,u sets the initial value). */
+int sonics_set_sort_bits(sonics_ctx *ctx, int eff_bits, int down_bits, int up_bits);
+/* Scratch for sonics_simulate / sonics_replay_best.  Lockstep form: sort keys and unit order, 24 bytes per work
+ * unit + CUB temporary storage.  Persistent form: the final PCR pools of the work units of one chunk (K1a -> K1b
+ * hand-off, 128 * max_window bytes per 32 units).  sonics_scratch_bytes(n_units, max_window) is the size that runs
+ * n_units = n_active * sim_count in a single chunk of the lockstep form, sonics_scratch_bytes_kernel(.., kernel)
+ * the same for a given form; anything from the size for 32 units up works (more chunks). */
 size_t sonics_scratch_bytes(int64_t n_units, int max_window);
+size_t sonics_scratch_bytes_kernel(int64_t n_units, int max_window, int kernel);
 
 /* ---- K2/K3: per-genotype statistics on the cumulative lnL arrays ---------
  * Restates sonics.pyx:136-191 (+ :208-252 for the final verdict): grouping,
@@ -196,6 +216,9 @@ int sonics_replay_best(sonics_ctx *ctx, const SonicsParams *params, const void *
  * caller-owned device buffer of >= sonics_genotype_work_bytes(...) bytes.
  * Synchronous (returns when verdict_out is filled). */
 size_t sonics_genotype_work_bytes(int n_gt, int n_alleles_total, int max_reps);
+/* The same for one mode: the default mode needs no identity / r^2 planes (10 instead of 22 bytes per simulation).
+ * A caller with many genotypes and a large -r picks its batch size from this (driver.run_batch_verdicts). */
+size_t sonics_genotype_work_bytes_mode(int n_gt, int n_alleles_total, int max_reps, int monte_carlo);
 int sonics_genotype_batch(sonics_ctx *ctx, const SonicsParams *params, int n_gt, const int32_t *allele_off,
                           const int32_t *allele, const int32_t *reads, const float *noise_coef, const uint32_t *uid,
                           int max_reps, uint64_t seed, SonicsVerdict *verdict_out, void *dev_work,
@@ -230,6 +253,12 @@ typedef struct {
     int32_t x;
 } SonicsTraceEntry;
 int sonics_debug_trace(sonics_ctx *ctx, SonicsTraceEntry *dev_trace, int32_t trace_cap, int32_t *dev_trace_len);
+/* sonics_debug_readout: while dev_readout is non-NULL, every simulation that draws a sequencing readout
+ * (sonics_simulate with dev_identity / dev_rsq, sonics_replay_best) also stores it, per window bin, at
+ * dev_readout[unit * max_window + c] (unit = genotype slot * sim_count + simulation; bin c = repeat count
+ * window origin + c).  tests/test_gpu_readout.py feeds these vectors to the oracle's identity / rsq() restatement
+ * (sonics.pyx:273-291,373-384) and requires bit-identical descriptors.  Pass NULL to switch it off. */
+int sonics_debug_readout(sonics_ctx *ctx, int32_t *dev_readout);
 int sonics_debug_philox(sonics_ctx *ctx, uint64_t seed, uint64_t sim, uint32_t uid, uint32_t stream_id, int n_blocks,
                         uint32_t *dev_out);
 int sonics_debug_pairs(sonics_ctx *ctx, uint64_t seed, uint64_t sim, uint32_t uid, int n_pairs, uint32_t *dev_out);

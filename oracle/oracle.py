@@ -111,6 +111,9 @@ def lib():
         L.oracle_one_repeat.restype = ctypes.c_int
         L.oracle_one_repeat.argtypes = [ctypes.c_void_p, ctypes.POINTER(OracleCfg), ctypes.c_void_p, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p]
+        L.oracle_descriptors.restype = None
+        L.oracle_descriptors.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                         ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         assert L.oracle_sizeof_cfg() == ctypes.sizeof(OracleCfg), (L.oracle_sizeof_cfg(), ctypes.sizeof(OracleCfg))
         assert L.oracle_sizeof_record() == RECORD_DTYPE.itemsize, (L.oracle_sizeof_record(), RECORD_DTYPE.itemsize)
         _lib = L
@@ -229,6 +232,17 @@ def mvhyperg(x, color):
     x = np.ascontiguousarray(x, dtype=np.int64)
     color = np.ascontiguousarray(color, dtype=np.int64)
     return float(lib().oracle_mvhyperg(x.ctypes.data, color.ctypes.data, int(x.shape[0])))
+
+
+def descriptors(alleles, readout):
+    """(identity, r_squared) of a sequencing readout against the input reads (sonics.pyx:373-384, rsq :273-291)."""
+    alleles = np.ascontiguousarray(alleles, dtype=np.int64)
+    readout = np.ascontiguousarray(readout, dtype=np.int64)
+    assert alleles.shape == readout.shape
+    ident, r2 = ctypes.c_double(0), ctypes.c_double(0)
+    lib().oracle_descriptors(alleles.ctypes.data, readout.ctypes.data, int(alleles.shape[0]), ctypes.byref(ident),
+                             ctypes.byref(r2))
+    return ident.value, r2.value
 
 
 def label(rec):

@@ -10,6 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsonics_b200.so")
 
 SENTINEL = -999999.0
+KERNEL_AUTO, KERNEL_PERSISTENT, KERNEL_LOCKSTEP = 0, 1, 2
 FILTER_PASS, FILTER_MWU_TEST, FILTER_BEST_RATIO, FILTER_PERCENTILE_RATIO, FILTER_NO_SUCCESS = 1, 2, 4, 8, 16
 
 
@@ -80,14 +81,20 @@ PROTOTYPES = {
     "sonics_table_bytes": (_SZ, [_I, _I]),
     "sonics_table_build": (_I, [_P, ctypes.POINTER(SonicsParams), _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "sonics_table_max_window": (_I, [_P]),
+    "sonics_table_release": (_I, [_P, _P]),
     "sonics_simulate": (_I, [_P, ctypes.POINTER(SonicsParams), _P, _I, _P, _I, _I64, _I64, _U64, _I64, _I64, _P, _P,
                              _P, _P, _P, _P, _SZ, _P]),
     "sonics_scratch_bytes": (_SZ, [_I64, _I]),
+    "sonics_scratch_bytes_kernel": (_SZ, [_I64, _I, _I]),
+    "sonics_set_kernel": (_I, [_P, _I]),
+    "sonics_set_sort_bits": (_I, [_P, _I, _I, _I]),
+    "sonics_debug_readout": (_I, [_P, _P]),
     "sonics_evaluate": (_I, [_P, ctypes.POINTER(SonicsParams), _P, _I, _P, _I, _I64, _I64, _P, _P, _P, _P, _I, _P, _P,
                              _SZ, _P]),
     "sonics_stats_scratch_bytes": (_SZ, [_I64, _I, _I]),
     "sonics_replay_best": (_I, [_P, ctypes.POINTER(SonicsParams), _P, _I, _P, _I, _U64, _P, _P, _SZ, _P]),
     "sonics_genotype_work_bytes": (_SZ, [_I, _I, _I]),
+    "sonics_genotype_work_bytes_mode": (_SZ, [_I, _I, _I, _I]),
     "sonics_genotype_batch": (_I, [_P, ctypes.POINTER(SonicsParams), _I, _P, _P, _P, _P, _P, _I, _U64, _P, _P, _SZ,
                                    _P]),
     "sonics_debug_counters": (_I, [_P, _P]),

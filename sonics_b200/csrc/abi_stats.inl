@@ -270,7 +270,7 @@ int sonics_replay_best(sonics_ctx *ctx, const SonicsParams *params, const void *
     a.rsq = nullptr;
     a.simpar = nullptr;
     a.replay = dev_verdict;
-    return launch_simulate(ctx, a, ti, true, n_active, dev_scratch, dev_scratch_bytes, stream);
+    return launch_simulate(ctx, a, ti, true, n_active, n_active, dev_scratch, dev_scratch_bytes, stream);
 }
 
 // device workspace of sonics_genotype_batch
@@ -305,13 +305,23 @@ static BatchLayout batch_layout(int n_gt, int n_alleles_total, int max_reps, int
     o += align_up((size_t)n_gt * 4, 256);
     L.off_count = o;
     o += 256;
-    // simulation scratch (final pools of one chunk of work units).  Window widths are not known before the
-    // table is built: size for the widest possible window of SONICS_MAX_ALLELE bins per 32 units at least,
-    // and for ~128 bins per unit of the largest round otherwise; smaller scratch only means more chunks.
+    // simulation scratch: sized so that the largest round of the schedule (sonics.pyx:79-82,193-199) runs as one
+    // chunk of the lockstep form (24 bytes per work unit + CUB storage), never below the smallest chunk of the
+    // persistent form for the widest possible window; smaller scratch would only mean more chunks.
     L.off_scratch = o;
-    const size_t want = 256 + (size_t)((int64_t)n_gt * std::min(max_reps, 512) + 31) / 32 * 64 * 32 * 4;
-    L.scratch_bytes = std::min<size_t>(std::max<size_t>(want, 256 + (size_t)SONICS_MAX_ALLELE * 32 * 4 * 8),
-                                       (size_t)1 << 31);
+    int64_t run = 0, biggest = 0, reps = monte_carlo ? max_reps : (max_reps > 100 ? 100 : max_reps);
+    for (int rnd = 1; run < max_reps; ++rnd) {
+        biggest = std::max(biggest, reps);
+        run += reps;
+        reps = (rnd % 2 == 1) ? 4 * run : run;
+        if (reps + run > max_reps)
+            reps = max_reps - run;
+    }
+    LsLayout ls;
+    const int64_t units = std::min<int64_t>((int64_t)n_gt * biggest, (int64_t)1 << 30);
+    L.scratch_bytes = scratch_bytes_for(32 * 8, SONICS_MAX_ALLELE);
+    if (ls_layout(units, ls) == 0)
+        L.scratch_bytes = std::max(L.scratch_bytes, ls.total);
     if (max_reps > SONICS_STATS_MAX_N) // the large-n statistics reuse the scratch between rounds
         L.scratch_bytes = std::max(L.scratch_bytes, stats_big_bytes(max_reps, SONICS_STATS_MAX_SLOTS));
     o += align_up(L.scratch_bytes, 256);
@@ -319,12 +329,17 @@ static BatchLayout batch_layout(int n_gt, int n_alleles_total, int max_reps, int
     return L;
 }
 
-size_t sonics_genotype_work_bytes(int n_gt, int n_alleles_total, int max_reps)
+size_t sonics_genotype_work_bytes_mode(int n_gt, int n_alleles_total, int max_reps, int monte_carlo)
 {
     if (n_gt <= 0 || n_alleles_total <= 0 || max_reps <= 0)
         return 0;
+    return batch_layout(n_gt, n_alleles_total, max_reps, monte_carlo ? 1 : 0).total;
+}
+
+size_t sonics_genotype_work_bytes(int n_gt, int n_alleles_total, int max_reps)
+{
     // sized for the larger (--monte_carlo) layout so one query serves both modes
-    return batch_layout(n_gt, n_alleles_total, max_reps, 1).total;
+    return sonics_genotype_work_bytes_mode(n_gt, n_alleles_total, max_reps, 1);
 }
 
 int sonics_genotype_batch(sonics_ctx *ctx, const SonicsParams *params, int n_gt, const int32_t *allele_off,
@@ -354,6 +369,11 @@ int sonics_genotype_batch(sonics_ctx *ctx, const SonicsParams *params, int n_gt,
     if (int rc = sonics_table_build(ctx, params, n_gt, allele_off, allele, reads, noise_coef, uid, d_table,
                                     sonics_table_bytes(n_gt, nA), stream))
         return rc;
+    struct TableGuard { // the table lives in the workspace: its host-side record goes away on every exit path
+        sonics_ctx *c;
+        const void *t;
+        ~TableGuard() { c->tables.erase(t); }
+    } table_guard{ctx, d_table};
     TableInfo ti;
     TableView tv;
     if (int rc = find_table(ctx, d_table, n_gt, ti, tv))
@@ -402,7 +422,6 @@ int sonics_genotype_batch(sonics_ctx *ctx, const SonicsParams *params, int n_gt,
     for (int g = 0; g < n_gt; ++g)
         if (verdict_out[g].best_sim == -2)
             return fail(SONICS_ERR_CUDA, "genotype %d: replay of the best simulation did not reproduce its lnL", g);
-    ctx->tables.erase(d_table);
     return SONICS_OK;
 }
 

@@ -20,6 +20,11 @@
 // Stirling evaluation is needed for well under 1% of trials at large n*p*q; uniforms are built
 // with integer ops and reciprocals 1/x of the inversion recurrence come from a shared-memory
 // table, which keeps conversions and MUFU ops off the saturated XU pipe.
+//
+// Rounding.  The same draw is made by two differently structured kernels (k_pcr, k_pcr_ls) that must agree bit
+// for bit, so wherever a product feeds a sum the fused / unfused choice is written out (fmaf, __fmul_rn,
+// __fadd_rn): left to the compiler's contraction it came out differently in the two kernels for one PTRS
+// expression (3.5e-5 of the simulations ended with another pool; r02 diagnosis).
 #pragma once
 #include "rng.cuh"
 
@@ -55,7 +60,7 @@ __device__ __forceinline__ float stirling_tail(float k)
 {
     const float r = rcp_fast(k + 1.0f);
     const float r2 = r * r;
-    return r * (0.083333333333f - r2 * (0.002777777778f - r2 * 0.000793650794f));
+    return r * fmaf(-r2, fmaf(-r2, 0.000793650794f, 0.002777777778f), 0.083333333333f);
 }
 
 // floor(x) for |x| < 2^22 without the XU pipe: round-down add of 1.5 * 2^23
@@ -118,11 +123,11 @@ __device__ __forceinline__ void btrs_setup(DrawState &s, int n, float p)
     const float lo = fmaf(s.fn, p, -hi);
     s.npq = hi * q;
     const float spq = sqrt_fast(s.npq);
-    s.b = 1.15f + 2.53f * spq;
+    s.b = fmaf(2.53f, spq, 1.15f);
     const float rb = rcp_fast(s.b);
-    s.a = -0.0873f + 0.0248f * s.b + 0.01f * p;
-    s.vr = 0.92f - 4.2f * rb;
-    s.alpha = (2.83f + 5.1f * rb) * spq;
+    s.a = fmaf(0.01f, p, fmaf(0.0248f, s.b, -0.0873f));
+    s.vr = fmaf(-4.2f, rb, 0.92f);
+    s.alpha = fmaf(5.1f, rb, 2.83f) * spq;
     s.ci = floorf(hi);                        // integer part of n*p (exact in fp32)
     s.cf = (hi - s.ci) + lo + 0.5f;           // c = n*p + 0.5 = ci + cf
     s.fm = s.ci + floorf(s.cf - 0.5f + p);    // m = floor((n+1) p)
@@ -145,12 +150,12 @@ __device__ __forceinline__ int btrs_trial(DrawState &s, uint32_t bits_a, uint32_
     s.A = log_fast(v * s.alpha * rcp_fast(fmaf(s.a * rus, rus, s.b)));
     const float d = s.fk - s.fm;
     const float ad = fabsf(d);
-    if (ad < 0.5f * s.npq - 1.0f) {
+    if (ad < fmaf(0.5f, s.npq, -1.0f)) {
         // BTPE step 5.2: t - rho <= ln f(k)/f(m) <= t + rho
         const float rn = rcp_fast(s.npq);
-        const float t = -0.5f * d * d * rn;
-        const float rho = (ad * rn) * (fmaf(ad, fmaf(ad, 0.33333333f, 0.625f), 0.16666667f) * rn + 0.5f);
-        const float eps = 1e-5f * (1.0f + fabsf(t)); // margin for the fp32 evaluation of A, t and rho
+        const float t = __fmul_rn(-0.5f * d * d, rn);
+        const float rho = __fmul_rn(ad * rn, fmaf(fmaf(ad, fmaf(ad, 0.33333333f, 0.625f), 0.16666667f), rn, 0.5f));
+        const float eps = fmaf(1e-5f, fabsf(t), 1e-5f); // margin for the fp32 evaluation of A, t and rho
         if (s.A < t - rho - eps)
             return 1;
         if (s.A > t + rho + eps)
@@ -170,11 +175,15 @@ __device__ __forceinline__ bool btrs_full(const DrawState &s)
     const float nk = s.fn - s.fk + 1.0f;
     const float k1 = s.fk + 1.0f;
     const float rk1 = rcp_fast(k1), rnk = rcp_fast(nk); // IEEE divisions cost ~10 instructions each here
-    const float t1 = (s.fm + 0.5f) * log1pf(-d * rk1);
-    const float t2 = (s.fn - s.fm + 0.5f) * log1pf(d * rnk);
-    const float t3 = d * logf(r * nk * rk1);
-    const float h = t1 + t2 + t3 + stirling_tail(s.fm) + stirling_tail(s.fn - s.fm) - stirling_tail(s.fk) -
-                    stirling_tail(s.fn - s.fk);
+    const float t1 = __fmul_rn(s.fm + 0.5f, log1pf(__fmul_rn(-d, rk1)));
+    const float t2 = __fmul_rn(s.fn - s.fm + 0.5f, log1pf(__fmul_rn(d, rnk)));
+    const float t3 = __fmul_rn(d, logf(__fmul_rn(r * nk, rk1)));
+    // products and sums rounded one by one, in this order (no contraction: see the header note)
+    float h = __fadd_rn(__fadd_rn(t1, t2), t3);
+    h = __fadd_rn(h, stirling_tail(s.fm));
+    h = __fadd_rn(h, stirling_tail(s.fn - s.fm));
+    h = __fsub_rn(h, stirling_tail(s.fk));
+    h = __fsub_rn(h, stirling_tail(s.fn - s.fk));
     return s.A <= h;
 }
 
@@ -234,8 +243,8 @@ __device__ __forceinline__ void pois_setup(DrawState &s, float lam) // lam >= 10
 {
     s.fn = lam;
     const float slam = sqrt_fast(lam);
-    s.b = 0.931f + 2.53f * slam;
-    s.a = -0.059f + 0.02483f * s.b;
+    s.b = fmaf(2.53f, slam, 0.931f);
+    s.a = fmaf(0.02483f, s.b, -0.059f);
     s.alpha = fmaf(1.1328f, rcp_fast(s.b - 3.4f), 1.1239f); // 1 / alpha
     s.vr = fmaf(-3.6224f, rcp_fast(s.b - 2.0f), 0.9277f);
     s.ci = floorf(lam);
@@ -260,10 +269,12 @@ __device__ __forceinline__ bool pois_trial(DrawState &s, uint32_t bits_a, uint32
     float rhs;
     if (fk >= 10.0f) {
         const float rk = rcp_fast(fk);
-        const float y = (s.fn - fk) * rk;
-        rhs = fk * (log1pf(y) - y) - 0.5f * log_fast(6.2831853f * fk) - rk * (0.083333333f - 0.0027777778f * rk * rk);
+        const float y = __fmul_rn(s.fn - fk, rk);
+        const float t1 = __fmul_rn(fk, log1pf(y) - y);
+        const float t3 = __fmul_rn(rk, fmaf(-0.0027777778f * rk, rk, 0.083333333f));
+        rhs = __fsub_rn(fmaf(-0.5f, log_fast(6.2831853f * fk), t1), t3);
     } else {
-        rhs = -s.fn + fk * log_fast(s.fn) - lgammaf(fk + 1.0f);
+        rhs = __fsub_rn(fmaf(fk, log_fast(s.fn), -s.fn), lgammaf(fk + 1.0f));
     }
     return lhs <= rhs;
 }

@@ -50,6 +50,7 @@
 #include <stdint.h>
 
 #include "../../include/sonics_b200.h"
+#include "finish.cuh"
 #include "lnl.cuh"
 #include "rng.cuh"
 #include "samplers.cuh"
@@ -113,9 +114,69 @@ struct SimArgs {
     SonicsTraceEntry *trace; // [unit][trace_cap]
     int32_t *trace_len;      // [unit] entries requested (may exceed trace_cap: the excess is not stored)
     int32_t trace_cap;
+    // optional readout dump (sonics_debug_readout): the simulated sequencing readout per window bin,
+    // [unit_base + unit][Wcap]
+    int32_t *readout_dump;
+    // lockstep kernel (sim_lockstep.cuh): the launch's work units in execution order (nullable = identity)
+    const uint32_t *order;
 };
+
+// descriptors of the readout -> the per-simulation arrays, or (replay mode, K4) the genotype's verdict
+__device__ __forceinline__ void finish_store(const SimArgs &a, int g, int64_t o, double like, double ident, float r2)
+{
+    if (a.replay) {
+        a.replay[g].identity = ident;
+        a.replay[g].r_squared = (double)r2;
+        if (a.replay[g].lnL != like)
+            a.replay[g].best_sim = -2; // replay diverged from the recorded simulation: surfaced by the host
+    } else {
+        if (a.identity)
+            a.identity[o] = ident;
+        if (a.rsq)
+            a.rsq[o] = r2;
+    }
+}
 enum { K1_CNT_PASSES = 0, K1_CNT_MODE0 = 1 /* .. +6: lanes per mode summed over passes */, K1_CNT_ADV_TRIPS = 8,
        K1_CNT_ADV_LANES = 9, K1_CNT_FULL_RUNS = 10, K1_CNT_FULL_LANES = 11, K1_CNT_WARPS = 12 };
+
+// generate_params (sonics.pyx:33-45) and the start alleles (:320-324) of simulation j of a genotype: the first
+// three blocks of the simulation's Philox4x32-10 stream.  One definition for every kernel that needs them (the
+// persistent and the lockstep simulation kernels, the sort-key kernel), so they agree bit for bit.
+struct Priors {
+    double down, up, cap, eff;
+    int i1, i2; // indices of the two start alleles in the genotype's allele list
+};
+__device__ __forceinline__ Priors draw_priors(const SimParamsDev &p, uint64_t seed, const GtHeader &h, int64_t j)
+{
+    Rng prior;
+    prior.init(seed, (uint64_t)j, h.uid, STREAM_MAIN);
+    const uint4 q0 = prior.block4(), q1 = prior.block4(), q2 = prior.block4();
+    Priors r;
+    // d, u, c, p in that order
+    // low + (high - low) * u, product and sum rounded separately as numpy's uniform() does
+    auto uni = [](double lo, double rng, double u) { return __dadd_rn(lo, __dmul_rn(rng, u)); };
+    r.down = uni(p.down_lo, p.down_rng, u01_53(q0.x, q0.y));
+    r.up = uni(p.up_lo, (p.up_preference ? p.up_hi : r.down) - p.up_lo, u01_53(q0.z, q0.w));
+    r.cap = uni(p.cap_lo, p.cap_rng, u01_53(q1.x, q1.y));
+    r.eff = uni(p.eff_lo, p.eff_rng, u01_53(q1.z, q1.w));
+    const uint32_t A = (uint32_t)h.n_alleles;
+    if (p.random_start) {
+        r.i1 = (int)__umulhi(q2.x, A);
+        r.i2 = (int)__umulhi(q2.y, A);
+    } else {
+        r.i1 = h.first_idx;
+        r.i2 = (int)__umulhi(q2.x, A);
+    }
+    return r;
+}
+
+// work unit u of a launch -> (slot, jrel): 32-bit division when it fits (the 64-bit one is a ~100-instruction call)
+__device__ __forceinline__ void unit_decode(const SimArgs &a, int u, int &slot, int &jrel)
+{
+    const int64_t gu = a.unit_base + u;
+    slot = gu < 0x7fffffffLL ? (int)((uint32_t)gu / (uint32_t)a.sims_per_gt) : (int)(gu / a.sims_per_gt);
+    jrel = (int)(gu - (int64_t)slot * a.sims_per_gt);
+}
 
 // fl_reads[i] = factln(reads[i]); hdr[g].fl_D = factln(D)
 __global__ void k_table_prep(GtHeader *hdr, const int32_t *reads, double *fl_reads, int n_gt, int n_alleles)
@@ -304,11 +365,8 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
                         } else {
                             u = (int)t;
                             tr_n = 0;
-                            const int64_t gu = a.unit_base + u;
-                            // 32-bit division when it fits (the 64-bit one is a ~100-instruction call)
-                            const int slot = gu < 0x7fffffffLL ? (int)((uint32_t)gu / (uint32_t)a.sims_per_gt)
-                                                               : (int)(gu / a.sims_per_gt);
-                            const int jrel = (int)(gu - (int64_t)slot * a.sims_per_gt);
+                            int slot, jrel;
+                            unit_decode(a, u, slot, jrel);
                             const int g = a.active ? a.active[slot] : slot;
                             const GtHeader h = a.t.hdr[g];
                             int64_t j = a.sim_begin + jrel;
@@ -321,32 +379,16 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
                             lo = h.lo;
                             floor_bin = h.floor_al - lo;
                             const int A = h.n_alleles;
-                            // generate_params (sonics.pyx:33-45): d, u, c, p in that order
-                            Rng prior;
-                            prior.init(a.seed, (uint64_t)j, h.uid, STREAM_MAIN);
-                            const uint4 q0 = prior.block4(), q1 = prior.block4(), q2 = prior.block4();
+                            const Priors pr = draw_priors(a.p, a.seed, h, j);
                             rng.init(a.seed, (uint64_t)j, h.uid); // the draws of the PCR cycles
-                            const double par_down = a.p.down_lo + a.p.down_rng * u01_53(q0.x, q0.y);
-                            const double par_up = a.p.up_preference
-                                                      ? a.p.up_lo + (a.p.up_hi - a.p.up_lo) * u01_53(q0.z, q0.w)
-                                                      : a.p.up_lo + (par_down - a.p.up_lo) * u01_53(q0.z, q0.w);
-                            const double par_cap = a.p.cap_lo + a.p.cap_rng * u01_53(q1.x, q1.y);
-                            const double par_eff = a.p.eff_lo + a.p.eff_rng * u01_53(q1.z, q1.w);
+                            const double par_down = pr.down, par_up = pr.up, par_cap = pr.cap, par_eff = pr.eff;
                             eff = (float)par_eff; // cdef float efficiency, capture (:401)
                             capture = (float)par_cap;
                             l_up = log1pf(-(float)par_up);   // ln(1 - up)
                             l_dn = log1pf(-(float)par_down); // ln(1 - down)
                             e1_up = expm1f(l_up);            // per-bin step of expm1(al * L)
                             e1_dn = expm1f(l_dn);
-                            // start alleles (:320-332)
-                            int i1, i2;
-                            if (a.p.random_start) {
-                                i1 = (int)__umulhi(q2.x, (uint32_t)A);
-                                i2 = (int)__umulhi(q2.y, (uint32_t)A);
-                            } else {
-                                i1 = h.first_idx;
-                                i2 = (int)__umulhi(q2.x, (uint32_t)A);
-                            }
+                            const int i1 = pr.i1, i2 = pr.i2; // start alleles (:320-332)
                             const int b1 = a.t.allele[h.a_off + i1] - lo;
                             const int b2 = a.t.allele[h.a_off + i2] - lo;
                             // initial pool (:326-337)
@@ -381,7 +423,14 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
                             pc = PC_SCAN;
                         }
                     }
-                    if (mode != M_EXIT) {
+                    if (mode != M_EXIT && cycle > n_cycles) {
+                        // n_cycles == 0 (range(1, 1) runs no cycle, sonics.pyx:410): the start pool is the result
+                        for (int c = 0; c < W; ++c)
+                            a.pool[pool_index(u, Wcap, c)] = hist[c * 32];
+                        if (TRACE && a.trace)
+                            a.trace_len[u] = tr_n;
+                        pc = PC_NEWSIM; // stays in M_BOUND: the next BOUNDARY pass pulls the next unit
+                    } else if (mode != M_EXIT) {
                         bool to_capture = false;
                         if (cycle == cap_cycle && !cap_done) {
                             // capture step (:412-423): max count, first non-zero allele, non-zero count
@@ -414,8 +463,8 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
                             carry = 0;
                             prev = b > 0 ? hist[(b - 1) * 32] : 0;
                             const float al = (float)(lo + b);
-                            E_up = expm1f(al * l_up);
-                            E_dn = expm1f(al * l_dn);
+                            E_up = expm1f(__fmul_rn(al, l_up));
+                            E_dn = expm1f(__fmul_rn(al, l_dn));
                         }
                         mode = M_ADV;
                         pc = PC_SCAN;
@@ -684,7 +733,6 @@ __global__ void __launch_bounds__(128) k_lnl(const SimArgs a)
         const int jrel = (int)(gu - (int64_t)slot * a.sims_per_gt);
         const int g = a.active ? a.active[slot] : slot;
         const GtHeader h = a.t.hdr[g];
-        const int W = h.W, lo = h.lo, A = h.n_alleles, D = h.D;
         int64_t j = a.sim_begin + jrel;
         if (a.replay) {
             j = a.replay[g].best_sim;
@@ -692,39 +740,17 @@ __global__ void __launch_bounds__(128) k_lnl(const SimArgs a)
                 continue;
         }
         int *col = a.pool + pool_index(u, Wcap, 0); // bin c of this simulation's pool is col[c * 32]
-        const int32_t *al = a.t.allele + h.a_off;
-        const int32_t *rd = a.t.reads + h.a_off;
-        const double *fl = a.t.fl_reads + h.a_off;
-
-        // sentinel: any reads[i] > pool[i] (:360-361); T = sum(pool)
-        bool sentinel = false;
-        for (int i = 0; i < A; ++i)
-            sentinel |= rd[i] > col[(al[i] - lo) * 32];
+        GtView gv;
+        gv.W = h.W;
+        gv.lo = h.lo;
+        gv.A = h.n_alleles;
+        gv.D = h.D;
+        gv.al = a.t.allele + h.a_off;
+        gv.rd = a.t.reads + h.a_off;
+        gv.fl = a.t.fl_reads + h.a_off;
+        gv.fl_D = h.fl_D;
         int T = 0;
-        for (int c = 0; c < W; ++c)
-            T += col[c * 32];
-        double like = SONICS_SENTINEL;
-        if (!sentinel) {
-            like = 0.0;
-            int ia = 0;
-            for (int c = 0; c < W; ++c) {
-                const int cnt = col[c * 32];
-                int xr = 0;
-                double flx = 0.0;
-                if (ia < A && al[ia] - lo == c) {
-                    xr = rd[ia];
-                    flx = fl[ia];
-                    ++ia;
-                }
-                if (cnt == 0)
-                    continue; // x == 0 too: the reference adds exact zeros
-                const double fc = factln_dev(cnt);
-                like = __dadd_rn(like, fc);
-                like = __dsub_rn(like, flx); // factln(0) = gammln(1) = 0.0 exactly in the reference
-                like = __dsub_rn(like, xr ? factln_dev(cnt - xr) : fc);
-            }
-            like = __dsub_rn(like, __dsub_rn(__dsub_rn(factln_dev(T), h.fl_D), factln_dev(T - D)));
-        }
+        const double like = pool_lnl(col, gv, T);
         const int64_t o = (int64_t)g * a.out_stride + a.out_offset + jrel;
         if (!a.replay)
             a.lnL[o] = like;
@@ -733,81 +759,11 @@ __global__ void __launch_bounds__(128) k_lnl(const SimArgs a)
             // own RNG stream: the main stream (and therefore lnL) is identical with or without it
             Rng rr;
             rr.init(a.seed, (uint64_t)j, h.uid, STREAM_READOUT);
-            // stage 1: n_i ~ Binomial(D, pool_i / T) for every bin (:354); the column is reused as storage
-            int N = 0;
-            const double invT = T > 0 ? 1.0 / (double)T : 0.0;
-            for (int c = 0; c < W; ++c) {
-                const int cnt = col[c * 32];
-                int ni = 0;
-                if (cnt != 0) {
-                    const uint4 w = rr.block4();
-                    ni = binomial(rr, D, (float)((double)cnt * invT), w.x, w.y, rcp_tab);
-                }
-                col[c * 32] = ni;
-                N += ni;
-            }
-            double ident = 0.0;
-            float r2 = -999999.0f;
-            if (N > 0) {
-                // stage 2: readout = bincount(choice(mid, D)) ~ Multinomial(D; n_i / N) (:368),
-                // drawn as a chain of conditional binomials
-                int R = D, M = N, fr = -1, to = -1, acc = 0, ia = 0;
-                for (int c = 0; c < W; ++c) {
-                    const int ni = col[c * 32];
-                    int xi = 0;
-                    if (ni > 0 && R > 0) {
-                        const uint4 w = rr.block4();
-                        xi = (ni == M) ? R : binomial(rr, R, __fdividef((float)ni, (float)M), w.x, w.y, rcp_tab);
-                    }
-                    R -= xi;
-                    M -= ni;
-                    col[c * 32] = xi;
-                    int xr = 0;
-                    if (ia < A && al[ia] - lo == c) {
-                        xr = rd[ia];
-                        ++ia;
-                    }
-                    acc += min(xr, xi);
-                    if (xr != 0 || xi != 0) {
-                        if (fr < 0)
-                            fr = c;
-                        to = c;
-                    }
-                }
-                ident = (double)acc / (double)D;
-                const double mean = (double)D / (double)(to - fr + 1);
-                double ss_tot = 0.0;
-                long long ss_res = 0;
-                ia = 0;
-                while (ia < A && al[ia] - lo < fr)
-                    ++ia;
-                for (int c = fr; c <= to; ++c) {
-                    int xr = 0;
-                    if (ia < A && al[ia] - lo == c) {
-                        xr = rd[ia];
-                        ++ia;
-                    }
-                    const int xi = col[c * 32];
-                    const double dl = (double)xr - mean;
-                    ss_tot = __dadd_rn(ss_tot, __dmul_rn(dl, dl));
-                    const long long e = (long long)xr - xi;
-                    ss_res += e * e;
-                }
-                if (ss_tot == 0.0)
-                    ss_tot = 1e-16;
-                r2 = (float)(1.0 - (double)ss_res / ss_tot);
-            }
-            if (a.replay) {
-                a.replay[g].identity = ident;
-                a.replay[g].r_squared = (double)r2;
-                if (a.replay[g].lnL != like)
-                    a.replay[g].best_sim = -2; // replay diverged from the recorded simulation: surfaced by the host
-            } else {
-                if (a.identity)
-                    a.identity[o] = ident;
-                if (a.rsq)
-                    a.rsq[o] = r2;
-            }
+            double ident;
+            float r2;
+            pool_readout(col, gv, T, rr, rcp_tab, ident, r2,
+                         a.readout_dump ? a.readout_dump + (size_t)gu * Wcap : nullptr);
+            finish_store(a, g, o, like, ident, r2);
         }
     }
 }

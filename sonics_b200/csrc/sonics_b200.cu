@@ -14,6 +14,7 @@
 
 #include "../../include/sonics_b200.h"
 #include "sim_kernel.cuh"
+#include "sim_lockstep.cuh"
 #include "stats_kernel.cuh"
 #include "stats_big.cuh"
 
@@ -54,6 +55,9 @@ struct sonics_ctx {
     SonicsTraceEntry *trace; // sonics_debug_trace
     int32_t *trace_len;
     int32_t trace_cap;
+    int32_t *readout_dump;   // sonics_debug_readout
+    int kernel;              // SONICS_KERNEL_*: which form of K1 sonics_simulate launches
+    int sort_bits[3];        // lockstep sort key: bits of efficiency / down / up (-1 = automatic)
     std::map<const void *, TableInfo> tables;
 };
 
@@ -99,6 +103,17 @@ int sonics_create(int device, sonics_ctx **out)
     c->trace = nullptr;
     c->trace_len = nullptr;
     c->trace_cap = 0;
+    c->readout_dump = nullptr;
+    c->kernel = SONICS_KERNEL_AUTO;
+    c->sort_bits[0] = c->sort_bits[1] = c->sort_bits[2] = -1;
+    if (const char *e = getenv("SONICS_K1")) { // measurement switch; tests use sonics_set_kernel
+        if (!strcmp(e, "persistent"))
+            c->kernel = SONICS_KERNEL_PERSISTENT;
+        else if (!strcmp(e, "lockstep"))
+            c->kernel = SONICS_KERNEL_LOCKSTEP;
+    }
+    if (const char *e = getenv("SONICS_SORT_BITS"))
+        sscanf(e, "%d,%d,%d", &c->sort_bits[0], &c->sort_bits[1], &c->sort_bits[2]);
     *out = c;
     return SONICS_OK;
 }
@@ -241,10 +256,10 @@ int sonics_table_build(sonics_ctx *ctx, const SonicsParams *params, int n_gt, co
         // floor-1 (:427,472); up-stutter walks one bin per cycle (:476)
         int lo = std::max(floor_al - 1, min_in - params->n_cycles);
         lo = std::max(0, std::min(lo, min_in));
-        const int hi = max_in + params->n_cycles;
-        if (hi >= SONICS_MAX_ALLELE)
-            return fail(SONICS_ERR_RANGE, "genotype %d: allele %d + %d cycles leaves the %d-bin histogram", g, max_in,
-                        params->n_cycles, SONICS_MAX_ALLELE);
+        // The reference's histogram ends at bin SONICS_MAX_ALLELE - 1 (:21); up-stutter out of that bin raises an
+        // IndexError there (:476).  Here the window is clamped to it and such molecules are dropped: a genotype
+        // near the end of the range is simulated like any other instead of failing the whole batch.
+        const int hi = std::min(max_in + params->n_cycles, SONICS_MAX_ALLELE - 1);
         GtHeader &h = hdr[g];
         h.a_off = a0;
         h.n_alleles = A;
@@ -281,6 +296,14 @@ int sonics_table_build(sonics_ctx *ctx, const SonicsParams *params, int n_gt, co
 
 int sonics_table_max_window(sonics_ctx *ctx) { return ctx ? ctx->max_W_last : 0; }
 
+int sonics_table_release(sonics_ctx *ctx, const void *dev_table)
+{
+    if (!ctx)
+        return fail(SONICS_ERR_ARG, "sonics_table_release: ctx is NULL");
+    ctx->tables.erase(dev_table);
+    return SONICS_OK;
+}
+
 static int find_table(sonics_ctx *ctx, const void *dev_table, int n_gt, TableInfo &ti, TableView &tv)
 {
     auto it = ctx->tables.find(dev_table);
@@ -297,17 +320,51 @@ static int find_table(sonics_ctx *ctx, const void *dev_table, int n_gt, TableInf
     return SONICS_OK;
 }
 
-// Scratch layout: [counters: 256 B][pool: ceil(units / 32) * Wcap * 32 int32]
+// Scratch of the persistent form: [counters: 256 B][pool: ceil(units / 32) * Wcap * 32 int32]
 static size_t scratch_bytes_for(int64_t n_units, int Wcap)
 {
     const int64_t tiles = (n_units + 31) / 32;
     return 256 + (size_t)tiles * Wcap * 32 * 4;
 }
 
-// Runs units [0, total_units) of `a` (unit -> (slot, jrel) as documented at SimArgs) in chunks that
-// fit the caller's scratch: per chunk one persistent k_pcr launch and one k_lnl launch.
-static int launch_simulate(sonics_ctx *ctx, SimArgs &a, const TableInfo &ti, bool readout, int64_t total_units,
-                           void *dev_scratch, size_t scratch_bytes, void *stream)
+// Scratch of the lockstep form: [counters: 256 B][keys x2: u64][units x2: u32][CUB temporary storage]
+struct LsLayout {
+    size_t off_k0, off_k1, off_v0, off_v1, off_tmp, tmp_bytes, total;
+};
+static int ls_layout(int64_t n, LsLayout &L)
+{
+    size_t o = 256;
+    L.off_k0 = o;
+    o += align_up((size_t)n * 8, 256);
+    L.off_k1 = o;
+    o += align_up((size_t)n * 8, 256);
+    L.off_v0 = o;
+    o += align_up((size_t)n * 4, 256);
+    L.off_v1 = o;
+    o += align_up((size_t)n * 4, 256);
+    L.off_tmp = o;
+    cub::DoubleBuffer<uint64_t> dk(nullptr, nullptr);
+    cub::DoubleBuffer<uint32_t> dv(nullptr, nullptr);
+    size_t tmp = 0;
+    if (cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)n, 0, 64) != cudaSuccess)
+        return -1;
+    L.tmp_bytes = align_up(tmp, 256) + 256;
+    L.total = o + L.tmp_bytes;
+    return 0;
+}
+
+static int bits_for(int64_t v) // bits that hold the values 0 .. v-1
+{
+    int b = 0;
+    while (((int64_t)1 << b) < v)
+        ++b;
+    return b;
+}
+
+// Persistent form (K1a k_pcr + K1b k_lnl): units [0, total_units) of `a` (unit -> (slot, jrel) as documented at
+// SimArgs) in chunks that fit the caller's scratch: per chunk one persistent k_pcr launch and one k_lnl launch.
+static int launch_simulate_persistent(sonics_ctx *ctx, SimArgs &a, const TableInfo &ti, bool readout,
+                                      int64_t total_units, void *dev_scratch, size_t scratch_bytes, void *stream)
 {
     cudaStream_t s = (cudaStream_t)stream;
     a.Wcap = ti.max_W;
@@ -315,6 +372,8 @@ static int launch_simulate(sonics_ctx *ctx, SimArgs &a, const TableInfo &ti, boo
     a.trace = ctx->trace;
     a.trace_len = ctx->trace_len;
     a.trace_cap = ctx->trace_cap;
+    a.readout_dump = ctx->readout_dump;
+    a.order = nullptr;
     auto pcr = (ctx->trace || ctx->dbg) ? k_pcr<true> : k_pcr<false>;
     if (!dev_scratch || scratch_bytes < scratch_bytes_for(32, a.Wcap))
         return fail(SONICS_ERR_SPACE, "simulation scratch of %zu bytes is below the minimum %zu", scratch_bytes,
@@ -356,11 +415,157 @@ static int launch_simulate(sonics_ctx *ctx, SimArgs &a, const TableInfo &ti, boo
     return SONICS_OK;
 }
 
-size_t sonics_scratch_bytes(int64_t n_units, int max_window)
+// Lockstep form (sim_lockstep.cuh): per chunk k_sort_keys + CUB radix sort + k_pcr_ls (lnL / readout fused).
+static int launch_simulate_lockstep(sonics_ctx *ctx, SimArgs &a, const TableInfo &ti, bool readout, int64_t total_units,
+                                    int n_slots, void *dev_scratch, size_t scratch_bytes, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    a.Wcap = ti.max_W;
+    a.dbg = nullptr;
+    a.trace = nullptr;
+    a.trace_len = nullptr;
+    a.trace_cap = 0;
+    a.readout_dump = ctx->readout_dump;
+    a.pool = nullptr;
+    // chunk size from the scratch
+    LsLayout L;
+    if (ls_layout(32, L))
+        return fail(SONICS_ERR_CUDA, "CUB temporary-storage query failed");
+    if (!dev_scratch || scratch_bytes < L.total)
+        return fail(SONICS_ERR_SPACE, "simulation scratch of %zu bytes is below the minimum %zu", scratch_bytes, L.total);
+    int64_t cap_units = std::min<int64_t>(total_units, (int64_t)1 << 30);
+    while (true) {
+        if (ls_layout(cap_units, L))
+            return fail(SONICS_ERR_CUDA, "CUB temporary-storage query failed");
+        if (L.total <= scratch_bytes)
+            break;
+        cap_units = std::max<int64_t>(32, (int64_t)((double)cap_units * (double)scratch_bytes / (double)L.total * 0.98));
+    }
+    // sort key: slot | group | efficiency | down | up
+    const int A = ti.max_A;
+    const int64_t n_groups = a.p.random_start ? (int64_t)A * A : A;
+    SortCfg sc;
+    sc.grp_bits = bits_for(n_groups);
+    const int slot_bits = bits_for(n_slots);
+    const double per_group = (double)a.sims_per_gt / (double)(a.p.random_start ? (int64_t)A * (A + 1) / 2 : A);
+    int pbits = 0;
+    while (pbits < 15 && per_group / (double)(1 << (pbits + 1)) >= 32.0)
+        ++pbits;
+    sc.eff_bits = (pbits + 1) / 2;
+    sc.dn_bits = (pbits - sc.eff_bits + 1) / 2;
+    sc.up_bits = pbits - sc.eff_bits - sc.dn_bits;
+    if (ctx->sort_bits[0] >= 0) {
+        sc.eff_bits = std::min(ctx->sort_bits[0], 15);
+        sc.dn_bits = std::min(std::max(ctx->sort_bits[1], 0), 15);
+        sc.up_bits = std::min(std::max(ctx->sort_bits[2], 0), 15);
+    }
+    // one simulation per genotype (K4 replay): the list is already in genotype order
+    const int key_bits = a.sims_per_gt == 1 ? 0 : slot_bits + sc.grp_bits + sc.eff_bits + sc.dn_bits + sc.up_bits;
+    if (key_bits > 64)
+        return fail(SONICS_ERR_RANGE, "sort key of %d bits", key_bits);
+
+    auto pcr = readout ? k_pcr_ls<true> : k_pcr_ls<false>;
+    const size_t per_warp = warp_smem_bytes(a.Wcap);
+    int wpb = (int)std::min<size_t>(4, (200 * 1024) / per_warp);
+    if (wpb < 1)
+        return fail(SONICS_ERR_RANGE, "window of %d bins does not fit shared memory", a.Wcap);
+    const size_t smem = SONICS_RCP_TABLE * 4 + per_warp * wpb;
+    CUDA_OK(cudaFuncSetAttribute(pcr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pcr, wpb * 32, smem));
+    if (occ < 1)
+        occ = 1;
+    unsigned char *base = (unsigned char *)dev_scratch;
+    a.counter = (unsigned int *)base;
+    for (int64_t u0 = 0; u0 < total_units; u0 += cap_units) {
+        const int64_t nu = std::min<int64_t>(cap_units, total_units - u0);
+        a.unit_base = u0;
+        a.n_units = (int32_t)nu;
+        CUDA_OK(cudaMemsetAsync(a.counter, 0, 256, s));
+        const int kgrid = (int)((nu + 255) / 256);
+        uint32_t *v0 = (uint32_t *)(base + L.off_v0), *v1 = (uint32_t *)(base + L.off_v1);
+        size_t tmp = L.tmp_bytes;
+        if (key_bits == 0) {
+            a.order = nullptr;
+        } else if (key_bits <= 32) {
+            uint32_t *k0 = (uint32_t *)(base + L.off_k0), *k1 = (uint32_t *)(base + L.off_k1);
+            k_sort_keys<uint32_t><<<kgrid, 256, 0, s>>>(a, sc, k0, v0);
+            cub::DoubleBuffer<uint32_t> dk(k0, k1);
+            cub::DoubleBuffer<uint32_t> dv(v0, v1);
+            CUDA_OK(cub::DeviceRadixSort::SortPairs(base + L.off_tmp, tmp, dk, dv, (int)nu, 0, key_bits, s));
+            a.order = dv.Current();
+            ctx->launches += 2;
+        } else {
+            uint64_t *k0 = (uint64_t *)(base + L.off_k0), *k1 = (uint64_t *)(base + L.off_k1);
+            k_sort_keys<uint64_t><<<kgrid, 256, 0, s>>>(a, sc, k0, v0);
+            cub::DoubleBuffer<uint64_t> dk(k0, k1);
+            cub::DoubleBuffer<uint32_t> dv(v0, v1);
+            CUDA_OK(cub::DeviceRadixSort::SortPairs(base + L.off_tmp, tmp, dk, dv, (int)nu, 0, key_bits, s));
+            a.order = dv.Current();
+            ctx->launches += 2;
+        }
+        CUDA_OK(cudaGetLastError());
+        const int64_t batches = (nu + 31) / 32;
+        const int64_t want = (batches + wpb - 1) / wpb;
+        const int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * occ);
+        pcr<<<grid, wpb * 32, smem, s>>>(a);
+        ctx->launches++;
+        CUDA_OK(cudaGetLastError());
+    }
+    return SONICS_OK;
+}
+
+static int launch_simulate(sonics_ctx *ctx, SimArgs &a, const TableInfo &ti, bool readout, int64_t total_units,
+                           int n_slots, void *dev_scratch, size_t scratch_bytes, void *stream)
+{
+    // the draw trace and the control-flow counters exist in the persistent form only
+    const bool persistent = ctx->kernel == SONICS_KERNEL_PERSISTENT || ctx->trace || ctx->dbg;
+    if (persistent)
+        return launch_simulate_persistent(ctx, a, ti, readout, total_units, dev_scratch, scratch_bytes, stream);
+    return launch_simulate_lockstep(ctx, a, ti, readout, total_units, n_slots, dev_scratch, scratch_bytes, stream);
+}
+
+size_t sonics_scratch_bytes_kernel(int64_t n_units, int max_window, int kernel)
 {
     if (n_units <= 0 || max_window <= 0)
         return 0;
-    return scratch_bytes_for(n_units, max_window);
+    if (kernel == SONICS_KERNEL_PERSISTENT)
+        return scratch_bytes_for(n_units, max_window);
+    LsLayout L;
+    if (ls_layout(n_units, L))
+        return 0;
+    return L.total;
+}
+
+size_t sonics_scratch_bytes(int64_t n_units, int max_window)
+{
+    return sonics_scratch_bytes_kernel(n_units, max_window, SONICS_KERNEL_LOCKSTEP);
+}
+
+int sonics_set_kernel(sonics_ctx *ctx, int kernel)
+{
+    if (!ctx || kernel < SONICS_KERNEL_AUTO || kernel > SONICS_KERNEL_LOCKSTEP)
+        return fail(SONICS_ERR_ARG, "sonics_set_kernel: bad argument");
+    ctx->kernel = kernel;
+    return SONICS_OK;
+}
+
+int sonics_set_sort_bits(sonics_ctx *ctx, int eff_bits, int down_bits, int up_bits)
+{
+    if (!ctx || eff_bits > 15 || down_bits > 15 || up_bits > 15)
+        return fail(SONICS_ERR_ARG, "sonics_set_sort_bits: bad argument");
+    ctx->sort_bits[0] = eff_bits;
+    ctx->sort_bits[1] = down_bits;
+    ctx->sort_bits[2] = up_bits;
+    return SONICS_OK;
+}
+
+int sonics_debug_readout(sonics_ctx *ctx, int32_t *dev_readout)
+{
+    if (!ctx)
+        return fail(SONICS_ERR_ARG, "sonics_debug_readout: ctx is NULL");
+    ctx->readout_dump = dev_readout;
+    return SONICS_OK;
 }
 
 int sonics_simulate(sonics_ctx *ctx, const SonicsParams *params, const void *dev_table, int n_gt,
@@ -405,7 +610,8 @@ int sonics_simulate(sonics_ctx *ctx, const SonicsParams *params, const void *dev
     a.simpar = dev_simpar;
     a.replay = nullptr;
     const bool readout = dev_identity != nullptr || dev_rsq != nullptr;
-    return launch_simulate(ctx, a, ti, readout, (int64_t)n_active * sim_count, dev_scratch, dev_scratch_bytes, stream);
+    return launch_simulate(ctx, a, ti, readout, (int64_t)n_active * sim_count, n_active, dev_scratch, dev_scratch_bytes,
+                           stream);
 }
 
 int sonics_debug_counters(sonics_ctx *ctx, uint64_t *dev_counters)

@@ -24,7 +24,8 @@ struct BigState { // device-resident scalars shared by the kernels of one genoty
     double high;        // max p so far
     int n_tests, pad2;
     double U;           // per-pair accumulators
-    unsigned long long tie;
+    unsigned long long tie; // sum over tie blocks of t^3 - t, exact while (n1 + n2)^3 < 2^64
+    double tie_d;           // the same sum in fp64 (scipy's tiecorrect works in float64) for larger samples
     double q[4];        // order statistics scratch
     double pct_ratio, best_ratio;
     double add_ratio[SONICS_MAX_ADD_RATIOS];
@@ -215,11 +216,19 @@ __global__ void k_big_ratio(BigBufs b, double qv, int dest /* -1: pct_ratio, els
         st.add_ratio[dest] = r;
 }
 
+// t^3 - t in fp64 with fixed rounding points (compared for equality across kernels)
+__device__ __forceinline__ double cube_minus(unsigned long long t)
+{
+    const double d = (double)t;
+    return __dsub_rn(__dmul_rn(__dmul_rn(d, d), d), d);
+}
+
 __global__ void k_big_pair_begin(BigBufs b)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         b.st->U = 0.0;
         b.st->tie = 0ull;
+        b.st->tie_d = 0.0;
     }
 }
 
@@ -229,7 +238,7 @@ __global__ void k_big_pair(BigBufs b, int target)
     const BigState &st = *b.st;
     if (!st.evaluated || target == st.best || b.cnt[target] == 0)
         return;
-    double u = 0.0;
+    double u = 0.0, tie_d = 0.0;
     unsigned long long tie = 0ull;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < st.n_heads; k += gridDim.x * blockDim.x) {
         const uint32_t hd = b.heads[k], en = b.heads[k + 1];
@@ -237,16 +246,19 @@ __global__ void k_big_pair(BigBufs b, int target)
         const unsigned long long tg = b.S[en] - b.S[hd];
         u += (double)tb * ((double)b.S[hd] + 0.5 * (double)tg);
         const unsigned long long t = tb + tg;
-        tie += t * t * t - t;
+        tie += t * t * t - t; // wraps for t > 2.6e6: k_big_pair_end then reads tie_d
+        tie_d += cube_minus(t);
     }
     // warp reduce, then one atomic per warp (U is a sum of multiples of 1/2 below 2^53: exact in any order)
     for (int o = 16; o > 0; o >>= 1) {
         u += __shfl_down_sync(0xffffffffu, u, o);
         tie += __shfl_down_sync(0xffffffffu, tie, o);
+        tie_d += __shfl_down_sync(0xffffffffu, tie_d, o);
     }
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(&b.st->U, u);
         atomicAdd(&b.st->tie, tie);
+        atomicAdd(&b.st->tie_d, tie_d);
     }
 }
 
@@ -259,10 +271,14 @@ __global__ void k_big_pair_end(BigBufs b, int target)
         return;
     const int n1 = b.cnt[st.best], n2 = b.cnt[target];
     const double N = (double)(n1 + n2);
-    const double tie_sum = (double)st.tie;
     ++st.n_tests;
-    if (st.tie == (unsigned long long)(n1 + n2) * (unsigned long long)(n1 + n2) * (unsigned long long)(n1 + n2) -
-                      (unsigned long long)(n1 + n2)) {
+    // N^3 - N fits 64 bits below N = 2^21; above that the fp64 sums are compared (one tie block of N values gives
+    // exactly the same expression on both sides)
+    const bool exact = n1 + n2 < (1 << 21);
+    const unsigned long long Nu = (unsigned long long)(n1 + n2);
+    const double tie_sum = exact ? (double)st.tie : st.tie_d;
+    const bool all_equal = exact ? st.tie == Nu * Nu * Nu - Nu : st.tie_d == cube_minus(Nu);
+    if (all_equal) {
         st.high = 1.0; // all values identical: ValueError in scipy 1.5.2 -> high_pval = 1 (sonics.pyx:175-176)
         return;
     }
@@ -353,7 +369,7 @@ __global__ void k_big_verdict(BigBufs b, const EvalArgs a, int g, int n)
         v.add_ratio[i] = st.add_ratio[i];
     const bool pass = high < a.padjust && st.pct_ratio > a.thr && st.best_ratio > a.thr;
     if (pass) {
-        v.filter = SONICS_FILTER_PASS;
+        v.filter = st.min_sim < 25 ? SONICS_FILTER_NO_SUCCESS : SONICS_FILTER_PASS; // :184-191 then :208, see k_evaluate
     } else if (a.final_round) {
         if (st.min_sim < 25) {
             v.filter = SONICS_FILTER_NO_SUCCESS;

@@ -510,7 +510,9 @@ __global__ void __launch_bounds__(SONICS_STATS_THREADS) k_evaluate(const EvalArg
         v.high_pval = high;
         const bool pass = high < a.padjust && pct_ratio > a.thr && best_ratio > a.thr;
         if (pass) {
-            v.filter = SONICS_FILTER_PASS;
+            // the loop breaks on success (:184-191) and the hard-coded `min_sim < 25` test still follows (:208):
+            // with --min_sim below 25 a passing genotype whose min_sim lies in [--min_sim, 25) ends as no_success
+            v.filter = min_sim < 25 ? SONICS_FILTER_NO_SUCCESS : SONICS_FILTER_PASS;
         } else if (a.final_round) {
             if (min_sim < 25) {
                 v.filter = SONICS_FILTER_NO_SUCCESS;
@@ -541,7 +543,7 @@ __global__ void __launch_bounds__(SONICS_STATS_THREADS) k_evaluate(const EvalArg
     }
 }
 
-// active' = genotypes of `active` whose verdict is not PASS (order preserved); *n_out = their count.
+// active' = genotypes of `active` whose verdict is not final yet (order preserved); *n_out = their count.
 // One block; runs between rounds of the repeat-until-pass loop.
 __global__ void k_compact_active(const int32_t *active_in, int n_in, const SonicsVerdict *verdict, int32_t *active_out,
                                  int32_t *n_out)
@@ -556,7 +558,8 @@ __global__ void k_compact_active(const int32_t *active_in, int n_in, const Sonic
         int g = -1, keep = 0;
         if (i < n_in) {
             g = active_in ? active_in[i] : i;
-            keep = !(verdict[g].filter & SONICS_FILTER_PASS);
+            // finished: passed, or passed with min_sim < 25 (no_success before the last round, see k_evaluate)
+            keep = !(verdict[g].filter & (SONICS_FILTER_PASS | SONICS_FILTER_NO_SUCCESS));
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;

@@ -228,6 +228,10 @@ def run_batch_verdicts(allele_off, allele, reads, noise, constants, ranges, opti
     n = len(noise)
     uids = np.arange(n, dtype=np.uint32) if uids is None else np.ascontiguousarray(uids, dtype=np.uint32)
     parts = []
+    # device batch: at most `chunk` genotypes, fewer when -r is large (workspace: 10 bytes per simulation, 22 with
+    # --monte_carlo, within the free device memory)
+    if n:
+        chunk = e.batch_size_for(n, int(allele_off[n]), options["repetitions"], options.get("monte_carlo"), chunk)
     for c0 in range(0, n, chunk):
         c1 = min(n, c0 + chunk)
         off = allele_off[c0:c1 + 1] - allele_off[c0]

@@ -4,6 +4,7 @@ PyTorch is plumbing only (device memory + streams); every computation happens in
 the CUDA library behind include/sonics_b200.h.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -79,13 +80,22 @@ TRACE_DTYPE = np.dtype([("kind", "<i4"), ("n", "<i4"), ("p", "<f4"), ("x", "<i4"
 class Table:
     """A genotype table resident in device memory (torch uint8 tensor owned here)."""
 
-    def __init__(self, buf, n_gt, allele_off, allele, reads, max_window):
+    def __init__(self, buf, n_gt, allele_off, allele, reads, max_window, owner=None):
+        self._owner = owner  # the Engine whose ctx holds the host-side record of this table
         self.buf = buf
         self.n_gt = n_gt
         self.allele_off = allele_off
         self.allele = allele
         self.reads = reads
         self.max_window = max_window
+
+    def __del__(self):
+        try:
+            e = self._owner
+            if e is not None and getattr(e, "ctx", None):
+                e.lib.sonics_table_release(e.ctx, self.buf.data_ptr())
+        except Exception:
+            pass
 
     def group_label(self, g, gid):
         """u16 group id -> 'lo/hi' label (sonics.pyx:329-332)."""
@@ -109,6 +119,16 @@ class Engine:
         ctx = ctypes.c_void_p()
         check(self.lib.sonics_create(self.device_index, ctypes.byref(ctx)))
         self.ctx = ctx
+        # mirrors the library's SONICS_K1 measurement switch (scratch sizing differs between the two forms of K1)
+        self.kernel = {"persistent": _abi.KERNEL_PERSISTENT, "lockstep": _abi.KERNEL_LOCKSTEP}.get(
+            os.environ.get("SONICS_K1", ""), _abi.KERNEL_AUTO)
+        self._pools_wanted = False
+
+    def set_kernel(self, kernel):
+        """Which form of K1 simulate() launches: 'auto' (lockstep unless tracing), 'persistent', 'lockstep'."""
+        k = {"auto": _abi.KERNEL_AUTO, "persistent": _abi.KERNEL_PERSISTENT, "lockstep": _abi.KERNEL_LOCKSTEP}[kernel]
+        check(self.lib.sonics_set_kernel(self.ctx, k))
+        self.kernel = k
 
     def close(self):
         if getattr(self, "ctx", None):
@@ -154,10 +174,12 @@ class Engine:
         trace = t.zeros(units * trace_cap * TRACE_DTYPE.itemsize, dtype=t.uint8, device=self.device)
         tlen = t.zeros(units, dtype=t.int32, device=self.device)
         check(self.lib.sonics_debug_trace(self.ctx, trace.data_ptr(), int(trace_cap), tlen.data_ptr()))
+        self._pools_wanted = True  # the traced (persistent) form leaves the final pools in the scratch
         try:
             out = self.simulate(params, table, sim_count, seed, sim_begin=sim_begin, simpar=True, out_offset=0)
             self.sync()
         finally:
+            self._pools_wanted = False
             check(self.lib.sonics_debug_trace(self.ctx, None, 0, None))
         W = table.max_window
         raw = self._scratch_buf[256:256 + ((units + 31) // 32) * W * 128].cpu().numpy().view(np.int32)
@@ -200,7 +222,7 @@ class Engine:
             self.ctx, ctypes.byref(params), n_gt, allele_off.ctypes.data, allele.ctypes.data, reads.ctypes.data,
             None if nc is None else nc.ctypes.data, None if ui is None else ui.ctypes.data, buf.data_ptr(),
             buf.numel(), self._stream()))
-        return Table(buf, n_gt, allele_off, allele, reads, self.lib.sonics_table_max_window(self.ctx))
+        return Table(buf, n_gt, allele_off, allele, reads, self.lib.sonics_table_max_window(self.ctx), owner=self)
 
     def build_table_from_arrays(self, params, genotypes, noise_coef=None, uid=None):
         off, al, rd = to_csr(genotypes)
@@ -243,9 +265,28 @@ class Engine:
     SCRATCH_CAP = 2 << 30  # bytes; larger jobs run in chunks
 
     def _scratch(self, n_units, max_window):
-        need = min(int(self.lib.sonics_scratch_bytes(int(n_units), int(max_window))), self.SCRATCH_CAP)
-        need = max(need, int(self.lib.sonics_scratch_bytes(32, int(max_window))))
+        persistent = self._pools_wanted or self.kernel == _abi.KERNEL_PERSISTENT
+        k = _abi.KERNEL_PERSISTENT if persistent else _abi.KERNEL_LOCKSTEP
+        need = min(int(self.lib.sonics_scratch_bytes_kernel(int(n_units), int(max_window), k)), self.SCRATCH_CAP)
+        # never below what either form needs for its smallest chunk (a counter / trace hook switches forms)
+        for kk in (_abi.KERNEL_PERSISTENT, _abi.KERNEL_LOCKSTEP):
+            need = max(need, int(self.lib.sonics_scratch_bytes_kernel(32, int(max_window), kk)))
         return self._scratch_bytes(need)
+
+    def simulate_with_readout_dump(self, params, table, sim_count, seed, sim_begin=0):
+        """simulate(readout=True) that also returns the simulated sequencing readouts (sonics_debug_readout):
+        (out, readout) with readout [n_gt, sim_count, max_window] int32 in window coordinates (host)."""
+        t = self.torch
+        units = table.n_gt * int(sim_count)
+        W = table.max_window
+        dump = t.zeros(units * W, dtype=t.int32, device=self.device)
+        check(self.lib.sonics_debug_readout(self.ctx, dump.data_ptr()))
+        try:
+            out = self.simulate(params, table, sim_count, seed, sim_begin=sim_begin, readout=True, out_offset=0)
+            self.sync()
+        finally:
+            check(self.lib.sonics_debug_readout(self.ctx, None))
+        return out, dump.cpu().numpy().reshape(table.n_gt, int(sim_count), W)
 
     def _scratch_bytes(self, need):
         s = getattr(self, "_scratch_buf", None)
@@ -301,7 +342,8 @@ class Engine:
         n_gt = len(allele_off) - 1
         nc = None if noise_coef is None else np.ascontiguousarray(noise_coef, dtype=np.float32)
         ui = None if uid is None else np.ascontiguousarray(uid, dtype=np.uint32)
-        nbytes = self.lib.sonics_genotype_work_bytes(n_gt, int(allele_off[-1]), int(max_reps))
+        nbytes = self.lib.sonics_genotype_work_bytes_mode(n_gt, int(allele_off[-1]), int(max_reps),
+                                                          int(params.monte_carlo))
         work = self._workspace(nbytes)
         out = np.zeros(n_gt, dtype=VERDICT_DTYPE)
         check(self.lib.sonics_genotype_batch(
@@ -309,6 +351,18 @@ class Engine:
             None if nc is None else nc.ctypes.data, None if ui is None else ui.ctypes.data, int(max_reps),
             int(seed) & 0xFFFFFFFFFFFFFFFF, out.ctypes.data, work.data_ptr(), work.numel(), self._stream()))
         return out
+
+    def batch_size_for(self, n_gt, n_alleles_total, max_reps, monte_carlo, want, fraction=0.6):
+        """Largest number of genotypes <= want whose genotype_batch workspace fits `fraction` of the free device
+        memory (a VCF with a large -r is run in several device batches instead of failing to allocate)."""
+        free, _ = self.torch.cuda.mem_get_info(self.device)
+        budget = int(free * fraction) + (self._work.numel() if getattr(self, "_work", None) is not None else 0)
+        per_gt = max(1, -(-int(n_alleles_total) // max(1, int(n_gt))))
+        b = max(1, min(int(want), int(n_gt)))
+        while b > 1 and int(self.lib.sonics_genotype_work_bytes_mode(b, b * per_gt, int(max_reps),
+                                                                     int(bool(monte_carlo)))) > budget:
+            b = (b + 1) // 2
+        return b
 
     def _workspace(self, nbytes):
         w = getattr(self, "_work", None)

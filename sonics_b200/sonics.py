@@ -191,7 +191,7 @@ def _monte_carlo_with_report(max_n_reps, constants, ranges, options):
         run += reps
         verdict = e.evaluate(params, table, out, run, final_round=run >= max_n_reps or mc)
         v = e.verdicts_to_host(verdict)[0]
-        if mc or (v["filter"] & 1):
+        if mc or (v["filter"] & (1 | 16)):  # PASS, or passed with min_sim < 25 -> no_success (sonics.pyx:208)
             break
         reps = 4 * run if rnd % 2 == 1 else run
         if reps + run > max_n_reps:

@@ -11,6 +11,8 @@ The outputs are committed; nothing at test time reads /root/reference.
                           -> pins oracle_one_repeat()/oracle_simulate() bit for bit
   monte_carlo_rows.json   sonics.monte_carlo() rows under np.random.seed(s)
                           -> pins oracle/stats.py (controller, MWU, quantiles, row format)
+  rsq.json                sonics.rsq() / identity on random (reads, readout) pairs
+                          -> pins oracle_descriptors() (and through it K1's readout descriptors)
   lnl_kat.json            lnL known-answer vectors: SURVEY.md 8(c) KAT-1..3 and
                           gammln spot values, plus mpmath 50-digit truths
 
@@ -313,6 +315,47 @@ def gen_prefilter():
     return {"cases": cases, "files": files}
 
 
+def gen_rsq():
+    """The reference's own rsq() (sonics.pyx:273-291) and the identity expression (:382-383) on random
+    (reads, readout) pairs, incl. ss_tot == 0 (flat reads -> the 1e-16 guard), readouts outside the span of
+    the reads, tiny totals.  r_squared is stored through a C float in one_repeat (:300): both forms are kept."""
+    rs = np.random.RandomState(20261020)
+    cases = []
+    for k in range(400):
+        reads = np.zeros(500, dtype=np.int64)
+        readout = np.zeros(500, dtype=np.int64)
+        a0 = int(rs.randint(1, 440))
+        n_al = int(rs.randint(1, 12))
+        idx = np.sort(rs.choice(np.arange(a0, a0 + 40), n_al, replace=False))
+        kind = k % 5
+        if kind == 0:      # flat reads on contiguous alleles: ss_tot == 0 when the readout stays inside
+            idx = np.arange(a0, a0 + n_al)
+            reads[idx] = int(rs.randint(1, 500))
+        elif kind == 1:    # tiny totals
+            reads[idx] = rs.randint(1, 4, n_al)
+        else:
+            reads[idx] = np.maximum(1, (10 ** rs.uniform(0, 3.7, n_al)).astype(np.int64))
+        D = int(reads.sum())
+        if kind == 0 and k % 2 == 0:
+            ridx = idx
+        else:
+            span = np.arange(max(1, idx[0] - int(rs.randint(0, 4))), min(499, idx[-1] + int(rs.randint(0, 4))) + 1)
+            ridx = span[rs.rand(len(span)) < 0.7]
+            if len(ridx) == 0:
+                ridx = span[:1]
+        w = rs.dirichlet(np.ones(len(ridx)) * 0.5)
+        readout[ridx] = rs.multinomial(D, w)
+        if readout.sum() == 0:
+            readout[ridx[0]] = D
+        r = float(ref.rsq(reads, readout))
+        nz = reads.nonzero()[0]
+        ident = sum([min(reads[i], readout[i]) for i in nz]) / sum(reads)
+        cases.append({"reads": {str(int(i)): int(reads[i]) for i in nz},
+                      "readout": {str(int(i)): int(readout[i]) for i in readout.nonzero()[0]},
+                      "rsq": r.hex(), "rsq_f32": float(np.float32(r)).hex(), "identity": float(ident).hex()})
+    return cases
+
+
 def dump(name, obj):
     with open(os.path.join(HERE, name), "w") as f:
         json.dump(obj, f, indent=0, separators=(",", ":"))
@@ -321,7 +364,9 @@ def dump(name, obj):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["rng", "one_repeat", "monte_carlo", "lnl", "vcf", "prefilter"]
+    which = sys.argv[1:] or ["rng", "one_repeat", "monte_carlo", "lnl", "vcf", "prefilter", "rsq"]
+    if "rsq" in which:
+        dump("rsq.json", gen_rsq())
     if "prefilter" in which:
         dump("prefilter.json", gen_prefilter())
     if "vcf" in which:

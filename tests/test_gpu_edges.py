@@ -77,11 +77,28 @@ def test_wide_window_and_high_alleles():
     assert abs((sel == -999999).mean() - (o == -999999).mean()) < 0.05
 
 
+def test_alleles_near_the_end_of_the_histogram_are_simulated():
+    """max allele + n_cycles >= 500: the window is clamped at bin 499 (the reference only fails if a molecule
+    actually stutters out of bin 499, which 18 consecutive up-stutters from 481 never do); the genotype is
+    simulated normally and does not fail the batch it is part of."""
+    e = engine()
+    params = eng.make_params()
+    gt = "480|10;481|20"
+    reads = orc.parse_reads(gt)
+    table = e.build_table_from_arrays(params, [orc.parse_reads(CFG1), reads], [0.0, 0.0])
+    out = e.simulate(params, table, 30000, seed=14)
+    e.sync()
+    lnL = out["lnL"][1].cpu().numpy()
+    grp = out["group"][1].cpu().numpy().view(np.uint16)
+    sel = lnL[grp == 0 * 2 + 1]  # 480/481
+    o = orc.run_parallel(orc.make_cfg(rng_mode=1, with_readout=False, force_second=480), reads, 15, 8000)["lnL"]
+    assert st.ks_2samp(sel, o).pvalue > 1e-3
+    assert abs((sel == -999999).mean() - (o == -999999).mean()) < 0.03
+
+
 def test_abi_error_paths():
     e = engine()
     params = eng.make_params()
-    with pytest.raises(SonicsError, match="leaves the 500-bin histogram"):
-        e.build_table_from_arrays(params, [orc.parse_reads("480|10;481|20")], [0.0])
     with pytest.raises(SonicsError, match="Less then two alleles"):
         e.build_table_from_arrays(params, [orc.parse_reads("9|10")], [0.0])
     with pytest.raises(SonicsError, match="overflows int32"):

@@ -298,3 +298,35 @@ def test_large_n_monte_carlo_mode_cfg3():
     assert v["r_squared_q75"] == stats.quantile_linear(np.sort(rsq[m]), 0.75)
     row = drop_in.format_row(v, {"monte_carlo": True}).split("\t")
     assert len(row) == 8 and row[7] == str(n)
+
+
+def test_pass_with_min_sim_below_25_is_no_success():
+    """--min_sim 5: a genotype that meets the PASS predicate while its weakest group has 12 valid simulations
+    leaves the loop (sonics.pyx:184-191) and is then reported by the hard-coded `min_sim < 25` test (:208) as
+    no_success with the repeats of that round -- the device verdict must say the same (and with the default
+    --min_sim 25 the same arrays are simply not evaluated yet)."""
+    e = engine()
+    t = e.torch
+    rs = np.random.RandomState(5)
+    reads = orc.parse_reads("9|10;10|10")
+    lnL = np.concatenate([-10 - rs.rand(60), -40 - rs.rand(12), np.full(28, -999999.0)])
+    gid = np.concatenate([np.zeros(60), np.ones(40)]).astype(np.uint16)
+    perm = rs.permutation(100)
+    lnL, gid = lnL[perm], gid[perm]
+    labels = np.where(gid == 0, "9/9", "9/10")
+    out = {"lnL": t.from_numpy(lnL.copy()).to(e.device).reshape(1, -1),
+           "group": t.from_numpy(gid.view(np.int16).copy()).to(e.device).reshape(1, -1)}
+    recs = [dict(identity=0.5, r_squared=0.5, lnL=float(x), label=str(l)) for x, l in zip(lnL, labels)]
+    it = iter([recs])
+    row, info = stats.monte_carlo(1000, lambda n: next(it), min_sim_opt=5)
+    assert row.split("\t")[0] == "./." and row.split("\t")[4] == "no_success" and row.split("\t")[8] == "100"
+    params = eng.make_params(min_sim=5)
+    table = e.build_table_from_arrays(params, [reads], [0.0])
+    v = e.verdicts_to_host(e.evaluate(params, table, out, 100, final_round=False))[0]
+    assert v["min_sim"] == 12 and v["run_reps"] == 100
+    assert v["filter"] == 16, v["filter"]          # SONICS_FILTER_NO_SUCCESS, not PASS
+    assert drop_in.format_row(v, {"monte_carlo": False, "add_ratios": ""}) == row
+    # default --min_sim 25: not evaluated in this round, no verdict yet
+    params = eng.make_params()
+    v = e.verdicts_to_host(e.evaluate(params, table, out, 100, final_round=False))[0]
+    assert v["filter"] == 0

@@ -50,11 +50,22 @@ SMP = marks(os.path.join(CSRC, "samplers.cuh"), [
 ])
 
 
+LS = marks(os.path.join(CSRC, "sim_lockstep.cuh"), [
+    ("ls_sort_keys", "__global__ void k_sort_keys", "// ---- lockstep samplers"),
+    ("ls_binomial", "int binomial_ls(", "int poisson_ls("),
+    ("ls_poisson", "int poisson_ls(", "// Shared memory: [rcp table]"),
+    ("ls_batch_setup", "// next batch of 32 units", "// ---- simulate (:397-480)"),
+    ("ls_capture", "// ---- simulate (:397-480)", "// ---- amplification sweep of this cycle"),
+    ("ls_sweep", "// ---- amplification sweep of this cycle", "// ---- lnL (+ readout) of the final pool"),
+    ("ls_finish", "// ---- lnL (+ readout) of the final pool", None),
+])
+
+
 def region(loc):
     if not loc:
         return "none"
     f, l = loc
-    tab = SIM if f == "sim_kernel.cuh" else SMP if f == "samplers.cuh" else None
+    tab = SIM if f == "sim_kernel.cuh" else SMP if f == "samplers.cuh" else LS if f == "sim_lockstep.cuh" else None
     if tab is None:
         return f
     for name, (a, b) in tab.items():
