@@ -13,11 +13,19 @@ same locus (weak scaling, no collective on the data path); rank 0 prints ONE JSO
   value  simulated PCR reactions/s, whole job, inputs resident in HBM, CUDA-event timed
   e2e    same metric through the public host API (genotype string in host memory -> table build
          + H2D -> simulate -> lnL/group arrays copied back to pinned host memory)
-  roofline        the HBM view the contract asks for (10 B/reaction of mandatory traffic) --
-                  this path is ALU-issue bound, so its frac is tiny by construction
-  issue_roofline  the bounding roofline: warp instructions issued per second
-                  against 148 SMs x 4 schedulers x SM clock; instructions/reaction come from the
-                  committed ncu capture (profiles/), the rate is measured live
+  roofline        the bounding roofline: warp instructions issued per second against
+                  148 SMs x 4 schedulers x SM clock.  Instructions per reaction come from the committed ncu
+                  capture (profiles/k1_counters.json, guarded by a hash of the kernel sources: a stale file
+                  gives frac = null), the rate is measured live.  lanes_active_of_32 and achieved_algorithmic
+                  (thread-instructions a simulation needs / thread-instruction peak) say how much of the
+                  issued work is useful; traffic = DRAM bytes of every kernel of the step
+  hbm_roofline    the HBM view (10 B/reaction of mandatory traffic): tiny by construction
+  configs         device-resident rates of cfg1 / cfg3, and cfg2 with the per-simulation readout
+                  (identity / r^2) switched on -- the work the reference's one_repeat() does
+  genotyping      the other half of BASELINE.json's metric, loci genotyped/s: cfg4 through the C-ABI with
+                  host buffers, a cfg5-style noisy VCF file to file across all ranks (strong scaling: seconds,
+                  genotypes/s, sha256 of the output) and, at N = 1, the reference's monte_carlo() on the host
+                  cores over a bounded subset of the same genotypes
   cpu_baseline    the reference's own one_repeat() (compiled from /root/reference/sonics.pyx into
                   oracle/_ref by oracle/build_ref.py) on the box's host cores, bounded sample
 
@@ -202,11 +210,13 @@ def genotyping_throughput(e, eng, drop_in, n_loci=10000, n_samples=8):
     from sonics_b200 import driver
     loci = synth_vcf.make_genotypes(n_loci, n_samples, seed=20261019, cov=(50, 1000))
     constants = {"one_allele_threshold": 45, "noise_threshold": 0.05}
-    work = []
+    work, items = [], []
     for t in synth_vcf.genotype_strings(loci):
         kind, payload = driver.prefilter(t, constants, {"monte_carlo": False})
         if kind == "sim":
             work.append(payload)
+            if len(items) < 4096:
+                items.append((t[3], payload[0], float(payload[1])))
     params = eng.make_params()
     off, al, rd = eng.to_csr([w[0] for w in work])
     noise = np.array([w[1] for w in work], dtype=np.float32)
@@ -239,7 +249,141 @@ def genotyping_throughput(e, eng, drop_in, n_loci=10000, n_samples=8):
             "file_to_file": {"value": n_lines / file_dt, "unit": "genotypes/s", "seconds": file_dt, "rows": n_lines,
                              "what": "sonics -m cfg4.vcf: native VCF ingest + pre-filters, GPU loop, native row writer"},
             "workload": "cfg4: synthetic VCF %d loci x %d samples, coverage 50-1000, -r 1000, default filters; "
-                        "host CSR in -> verdicts out through sonics_genotype_batch" % (n_loci, n_samples)}
+                        "host CSR in -> verdicts out through sonics_genotype_batch" % (n_loci, n_samples)}, items
+
+
+K1_SOURCES = ["sim_lockstep.cuh", "sim_kernel.cuh", "samplers.cuh", "rng.cuh", "finish.cuh", "lnl.cuh"]
+
+
+def kernel_sha():
+    """Hash of the K1 sources: profiles/k1_counters.json is only valid for the code it was captured from."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in K1_SOURCES:
+        with open(os.path.join(ROOT, "sonics_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def _geno_ref_worker(args):
+    """monte_carlo() of the compiled reference (or of the oracle port) over a list of pre-filtered genotypes."""
+    items, seed, kind = args
+    import numpy as np
+    if kind == "reference":
+        sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+        import sonics as ref
+    else:
+        from oracle import oracle as orc
+        from oracle import stats
+    ranges = ((0, 0.1), (0, 0.1), (-0.25, 0.25), (0.001, 0.1))
+    options = dict(repetitions=1000, out_path=".", strict=1, file_name="x", vcf_mode=True, name="s", block="b",
+                   processes=0, verbose=False, save_report=False, monte_carlo=False, add_ratios="", min_sim=25)
+    np.random.seed(seed)
+    t0 = time.perf_counter()
+    reps = 0
+    for gt, reads, nc in items:
+        if kind == "reference":
+            constants = dict(random=False, n_cycles=24, capture_cycle=13, up_preference=False, floor=5,
+                             lnL_threshold=2.3, start_copies=300000, genotype=gt, padjust=0.001, noise_threshold=0.05,
+                             one_allele_threshold=45, max_allele=500, genotype_total=int(reads.sum()), alleles=reads,
+                             noise_coef=nc)
+            row = ref.monte_carlo(1000, constants, ranges, options)
+        else:
+            cfg = orc.make_cfg(noise_coef=nc, rng_mode=0, with_readout=True)
+            state = {"k": 0}
+
+            def draw(n, cfg=cfg, reads=reads, state=state):
+                state["k"] += 1
+                recs = orc.run(cfg, reads, seed * 1000 + state["k"], n)
+                return [dict(identity=r["identity"], r_squared=r["r_squared"], lnL=r["lnL"], label=orc.label(r))
+                        for r in recs]
+            row, _ = stats.monte_carlo(1000, draw)
+        reps += int(row.split("\t")[8])
+    return time.perf_counter() - t0, reps
+
+
+def genotyping_cpu_baseline(work_items, target_s=15.0):
+    """The reference's monte_carlo() (sonics.pyx:47-269) over the first genotypes of the cfg4 VCF, one fork-pool
+    worker per host core (the reference's own -p strategy, sonics:216-221), sized for ~target_s seconds."""
+    kind = "reference" if have_ref() else "port"
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    # calibrate on one genotype per core, then take as many as fit the time budget (at least two per core)
+    with ctx.Pool(cores) as pool:
+        t = pool.map(_geno_ref_worker, [([work_items[i]], 1 + i, kind) for i in range(cores)])
+    per = max(1e-3, sum(x[0] for x in t) / cores)
+    per_core = int(max(2, min(40, target_s / per)))
+    n = min(len(work_items), cores * per_core)
+    jobs = [(work_items[i::cores][:per_core], 100 + i, kind) for i in range(cores)]
+    with ctx.Pool(cores) as pool:
+        t = pool.map(_geno_ref_worker, jobs)
+    secs = max(x[0] for x in t)
+    n = sum(len(j[0]) for j in jobs)
+    return {"value": n / secs, "unit": "genotypes/s", "cores": cores, "kind": kind,
+            "sample": "monte_carlo() on the first %d genotypes of the cfg4 VCF, %d per process on %d processes "
+                      "(%.1f s); a full-file figure would be this rate extrapolated" % (n, per_core, cores, secs),
+            "reactions": int(sum(x[1] for x in t)), "seconds": secs}
+
+
+def cfg5_subset_vcf(path, distinct_loci=2500, copies=10, n_samples=32):
+    """cfg5-style input (BASELINE.json configs[4]: coverage 2000-10000, 10 % noisy profiles -> no_success /
+    MWU_test at 1000 repetitions), `copies` x `distinct_loci` loci x 32 samples: the distinct profiles are
+    generated once and written `copies` times under different locus names (different RNG keys), which keeps
+    the generator out of the benchmark's run time."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import synth_vcf
+    loci = synth_vcf.make_genotypes(distinct_loci, n_samples, seed=20261019, cov=(2000, 10000), noisy=0.1)
+    tmp = path + ".block"
+    with open(path, "wb") as out:
+        for c in range(copies):
+            synth_vcf.write_vcf(tmp, loci, n_samples, start=c * distinct_loci, header=(c == 0))
+            with open(tmp, "rb") as f:
+                out.write(f.read())
+    os.unlink(tmp)
+    return distinct_loci * copies * n_samples
+
+
+def genotyping_file_to_file(rank, world, barrier, workdir):
+    """Strong scaling of the genotyping job: one cfg5-style VCF -> sonics_out.txt across all ranks
+    (driver.run_sonics under torchrun: round-robin byte pieces, no collective on the data path)."""
+    import hashlib
+    import logging
+    from sonics_b200 import driver
+    vcf = os.path.join(workdir, "cfg5_subset.vcf")
+    warm = os.path.join(workdir, "warm.vcf")
+    n_gt = 0
+    if rank == 0:
+        n_gt = cfg5_subset_vcf(vcf)
+        cfg5_subset_vcf(warm, distinct_loci=64, copies=1)
+    barrier()
+    logging.disable(logging.WARNING)
+    out = {}
+    for name, path in (("warm", warm), ("run", vcf)):
+        d = os.path.join(workdir, "out_" + name)
+        args = driver.build_parser().parse_args(["-m", path, "-o", d, "--seed", "20261019"])
+        c, r, o = driver.dicts_from_args(args)
+        barrier()
+        t0 = time.perf_counter()
+        driver.run_sonics(path, c, r, o, seed=20261019)
+        barrier()
+        out[name] = (time.perf_counter() - t0, os.path.join(d, "sonics_out.txt"))
+    logging.disable(logging.NOTSET)
+    secs, path = out["run"]
+    if rank != 0:
+        return None
+    h = hashlib.sha256()
+    rows = -1
+    with open(path, "rb") as f:
+        for blk in iter(lambda: f.read(1 << 22), b""):
+            h.update(blk)
+            rows += blk.count(b"\n")
+    return {"value": rows / secs, "unit": "genotypes/s", "n_gpus": world, "seconds": secs, "rows": rows,
+            "output_sha256": h.hexdigest(), "scaling": "strong",
+            "workload": "cfg5-style VCF: 25000 loci (2500 distinct profiles x 10) x 32 samples, coverage "
+                        "2000-10000, 10 %% noisy profiles, -r 1000, default filters; VCF file -> sonics_out.txt "
+                        "across %d rank(s), wall clock between barriers" % world,
+            "timings_rank0": {k: (round(v, 3) if isinstance(v, float) else v)
+                              for k, v in driver.LAST_TIMINGS.items()}}
 
 
 def main():
@@ -344,6 +488,60 @@ def main():
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(times[0]), float(times[1])
 
+    # ---- other single-locus configurations and the readout arm (rank 0, device-resident, 1 warm-up + 2 timed) ----
+    def timed_rate(spec, kw, nn, readout=False):
+        import math  # noqa: F401
+        from sonics_b200 import driver
+        kind, (reads, nc) = driver.prefilter(("s", "b", ".", spec), {"one_allele_threshold": 45,
+                                                                    "noise_threshold": 0.05}, {"monte_carlo": True})
+        pr = eng.make_params(**kw)
+        tb = e.build_table_from_arrays(pr, [reads], [float(np.float32(nc))])
+        o = e.simulate(pr, tb, nn, seed=5, readout=readout)
+        e.sync()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.zero_()
+        a.record()
+        for k in range(2):
+            e.simulate(pr, tb, nn, seed=6 + k, readout=readout, out=o)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 2
+        return {"reactions_per_s": nn / ms * 1e3, "ms_per_launch": ms, "reactions_per_launch": nn,
+                "window_bins": int(tb.max_window)}
+
+    configs = None
+    if rank == 0:
+        import math
+        cfg3 = ";".join("%d|%d" % (a, int(5 + 400 * math.exp(-0.5 * ((a - 28) / 6) ** 2) +
+                                          300 * math.exp(-0.5 * ((a - 36) / 5) ** 2))) for a in range(10, 50))
+        configs = {
+            "cfg1": dict(timed_rate("8|5;9|113;10|89", {}, n // 2), what="README example, defaults"),
+            "cfg3": dict(timed_rate(cfg3, dict(n_cycles=30, capture_cycle=16), n // 16),
+                         what="40 input alleles, 30 cycles, capture at 16, automatic noise"),
+            "cfg2_with_readout": dict(timed_rate(CFG2, {}, n // 2, readout=True),
+                                      what="cfg2 with the per-simulation sequencing readout, identity and r^2 "
+                                           "(sonics.pyx:341-384) -- everything the reference's one_repeat() does"),
+        }
+
+    # ---- genotyping: strong scaling of a cfg5-style VCF, file to file, across all ranks ----
+    geno_scale = None
+    if not args.no_genotyping:
+        import shutil
+        import tempfile
+        workdir = None
+        if rank == 0:
+            workdir = tempfile.mkdtemp(prefix="sonics_bench_")
+        if world > 1:
+            box = [workdir]
+            dist.broadcast_object_list(box, src=0)
+            workdir = box[0]
+        try:
+            geno_scale = genotyping_file_to_file(rank, world, barrier, workdir)
+        finally:
+            barrier()
+            if rank == 0:
+                shutil.rmtree(workdir, ignore_errors=True)
+
     if rank == 0:
         total = float(n) * world * args.steps
         value = total / (dev_ms * 1e-3)
@@ -354,42 +552,65 @@ def main():
             peaks = json.load(open(pk))
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         achieved_gbs = n * BYTES_PER_REACTION / (kernel_ms * 1e-3) / 1e9
+        sm_mhz = clk.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+        peak_issue = 148 * 4 * sm_mhz * 1e6  # warp instructions / s at the clock seen during the run
+        roof = {"bound": "alu_issue", "achieved": None, "peak": peak_issue, "unit": "warp-inst/s", "frac": None,
+                "traffic": None, "peak_source": "148 SMs x 4 schedulers x SM clock sampled during the run"}
+        cnt = load_inst_per_reaction()
+        sha = kernel_sha()
+        if cnt and cnt.get("kernel_sha") == sha:
+            ach = cnt["warp_inst_per_reaction"] * n / (kernel_ms * 1e-3)
+            roof.update({
+                "achieved": ach, "frac": ach / peak_issue,
+                "warp_inst_per_reaction": cnt["warp_inst_per_reaction"],
+                "lanes_active_of_32": cnt.get("avg_active_threads"),
+                # thread-instructions one simulation needs on its own (no idle lanes) against the thread-instruction
+                # peak: reactions/s x I_min / (peak_issue x 32)
+                "achieved_algorithmic": {
+                    "I_min_thread_inst_per_reaction": cnt.get("thread_inst_per_reaction"),
+                    "frac": (cnt.get("thread_inst_per_reaction", 0.0) * n / (kernel_ms * 1e-3)) / (peak_issue * 32),
+                    "per_config": cnt.get("per_config")},
+                "traffic": cnt.get("dram_bytes_per_reaction", 0.0) * n if cnt.get("dram_bytes_per_reaction") else None,
+                "traffic_note": "DRAM bytes of every kernel of the step (k_sort_keys + radix sort + k_pcr_ls) from "
+                                "ncu, per reaction x reactions of this step",
+                "source": cnt.get("source"), "kernel_sha": sha})
+        else:
+            roof["note"] = ("profiles/k1_counters.json is %s: instructions per reaction unknown for this build "
+                            "(kernel sources hash %s)" % ("missing" if not cnt else "stale (captured from %s)"
+                                                          % cnt.get("kernel_sha"), sha))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64 lnL / f32+int32 sampling", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32 samplers / int32 counts / f64 lnL", "data": "synthetic",
             "config": {"workload": "cfg2: single locus %s, default constants (24 cycles, capture at 13, 300000 start "
-                                   "copies), fixed-count simulation, %d reactions per step per GPU" % (CFG2, n),
-                       "l2": "flushed between steps (256 MiB memset, untimed)", "seed": 20261019},
+                                   "copies), fixed-count simulation without the per-simulation readout (genotyping "
+                                   "replays it for the reported row only), %d reactions per step per GPU" % (CFG2, n),
+                       "l2": "flushed between steps (256 MiB memset, untimed)", "seed": 20261019,
+                       "kernel": "lockstep (sort by priors + 32 similar simulations per warp)"},
             "e2e": {"value": total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved_gbs / hbm_peak, "traffic": None,
-                         "peak_source": "measured" if peaks else "fallback",
-                         "note": "K1 is ALU-issue bound: %d B/reaction of mandatory HBM traffic; see issue_roofline"
-                                 % BYTES_PER_REACTION},
+            "roofline": roof,
+            "hbm_roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": achieved_gbs / hbm_peak, "peak_source": "measured" if peaks else "fallback",
+                             "note": "%d B/reaction of mandatory HBM traffic: not the bound" % BYTES_PER_REACTION},
             "wall_s_timed_region": t_wall,
             "sentinel_fraction": frac_sentinel,
+            "configs": configs,
         }
-        cnt = load_inst_per_reaction()
-        if cnt:
-            sm_mhz = clk.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
-            peak_issue = 148 * 4 * sm_mhz * 1e6  # warp instructions / s at the clock seen during the run
-            ach = cnt["warp_inst_per_reaction"] * n / (kernel_ms * 1e-3)
-            line["roofline"]["traffic"] = cnt.get("dram_bytes_per_launch")
-            line["issue_roofline"] = {
-                "bound": "alu_issue", "achieved": ach, "peak": peak_issue, "unit": "warp-inst/s", "frac": ach / peak_issue,
-                "warp_inst_per_reaction": cnt["warp_inst_per_reaction"],
-                "lanes_active_of_32": cnt.get("avg_active_threads"),
-                "note": "frac counts issued warp-instructions (ncu count x live rate); the lanes doing useful work "
-                        "per instruction are lanes_active_of_32",
-                "source": cnt.get("source")}
+        geno = {}
+        items = None
         if world == 1 and not args.no_genotyping:
-            line["genotyping"] = genotyping_throughput(e, eng, drop_in)
+            geno, items = genotyping_throughput(e, eng, drop_in)
+        if geno_scale:
+            geno["strong_scaling"] = geno_scale
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
+            if items:
+                geno["cpu_baseline"] = genotyping_cpu_baseline(items)
+        if geno:
+            line["genotyping"] = geno
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -299,6 +299,10 @@ int sonics_vcf_fill(const sonics_vcf *vcf, int32_t *allele_off, int32_t *allele,
                     int32_t *row_kind);
 int sonics_vcf_uids(const sonics_vcf *vcf, int64_t line_base, uint32_t *uid_out);
 int sonics_vcf_lines_before(const char *path, int64_t byte_end, int64_t *n_lines);
+/* Data lines whose first byte lies in [byte_begin, byte_end) (< 0: end of file) = the blocks
+ * sonics_vcf_parse_range(path, byte_begin, byte_end) yields; a memchr scan of that range only.  The ranks of a
+ * multi-GPU run count their own pieces and exchange the counts to learn every piece's line_base. */
+int sonics_vcf_count_lines(const char *path, int64_t byte_begin, int64_t byte_end, int64_t *n_lines);
 const char *sonics_vcf_warning(const sonics_vcf *vcf, int64_t i);
 int sonics_rows_write(const char *path, const sonics_vcf *vcf, const SonicsVerdict *verdicts, int64_t n_verdicts,
                       int monte_carlo, const char *add_ratios, const char *name, const char *block);

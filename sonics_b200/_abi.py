@@ -111,6 +111,7 @@ PROTOTYPES = {
     "sonics_vcf_fill": (_I, [_P, _P, _P, _P, _P, _P]),
     "sonics_vcf_uids": (_I, [_P, _I64, _P]),
     "sonics_vcf_lines_before": (_I, [ctypes.c_char_p, _I64, ctypes.POINTER(_I64)]),
+    "sonics_vcf_count_lines": (_I, [ctypes.c_char_p, _I64, _I64, ctypes.POINTER(_I64)]),
     "sonics_vcf_warning": (ctypes.c_char_p, [_P, _I64]),
     "sonics_rows_write": (_I, [ctypes.c_char_p, _P, _P, _I64, _I, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]),
     "sonics_rows_write_part": (_I, [ctypes.c_char_p, _P, _P, _I64, _I, ctypes.c_char_p, ctypes.c_char_p,
@@ -125,11 +126,12 @@ def load():
     """Load libsonics_b200.so (raises ImportError when it has not been built)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("SONICS_B200_LIB", LIB_PATH)  # another build of the same ABI (kernel A/B runs)
+        if not os.path.exists(path):
             raise ImportError(
                 "sonics_b200: %s is missing -- build it with `python -m sonics_b200.build` "
-                "(there is no CPU fallback)" % LIB_PATH)
-        lib = ctypes.CDLL(LIB_PATH)
+                "(there is no CPU fallback)" % path)
+        lib = ctypes.CDLL(path)
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(lib, name)  # AttributeError if the symbol is not exported
             fn.restype = res

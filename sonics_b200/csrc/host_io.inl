@@ -12,6 +12,11 @@
 //   sonics_rows_write  the header (sonics:174-207), the row format of monte_carlo()
 //                      (sonics.pyx:122-134, 208-269) and "name\tblock\tref\trow\n" (sonics:437),
 //                      numbers printed like Python's str(float) (shortest repr).
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <charconv>
 #include <cstdlib>
 #include <fstream>
@@ -523,6 +528,56 @@ int sonics_vcf_lines_before(const char *path, int64_t byte_end, int64_t *n_lines
         }
     }
     fclose(fp);
+    *n_lines = count;
+    return SONICS_OK;
+}
+
+/* Number of data lines whose FIRST byte lies in [byte_begin, byte_end) (byte_end < 0: end of file) -- the lines
+ * sonics_vcf_parse_range(path, byte_begin, byte_end) turns into blocks.  memchr over a mapping of the file, so the
+ * ranks of a multi-GPU run can count their own pieces in parallel and exchange the counts (the line_base of piece
+ * k is the sum over the pieces before it) instead of each scanning the file from the start. */
+int sonics_vcf_count_lines(const char *path, int64_t byte_begin, int64_t byte_end, int64_t *n_lines)
+{
+    if (!path || !n_lines || byte_begin < 0)
+        return fail(SONICS_ERR_ARG, "sonics_vcf_count_lines: bad argument");
+    *n_lines = 0;
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0)
+        return fail(SONICS_ERR_ARG, "sonics_vcf_count_lines: cannot open %s", path);
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) {
+        close(fd);
+        return fail(SONICS_ERR_ARG, "sonics_vcf_count_lines: cannot stat %s", path);
+    }
+    const int64_t size = (int64_t)sb.st_size;
+    const int64_t end = (byte_end < 0 || byte_end > size) ? size : byte_end;
+    if (size == 0 || byte_begin >= end) {
+        close(fd);
+        return SONICS_OK;
+    }
+    const char *m = (const char *)mmap(nullptr, (size_t)size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED)
+        return fail(SONICS_ERR_ARG, "sonics_vcf_count_lines: cannot map %s", path);
+    // first line start at or after byte_begin
+    int64_t p = byte_begin;
+    if (p > 0 && m[p - 1] != '\n') {
+        const char *nl = (const char *)memchr(m + p, '\n', (size_t)(size - p));
+        p = nl ? (int64_t)(nl - m) + 1 : size;
+    }
+    int64_t count = 0;
+    while (p < end) {
+        const char c0 = m[p];
+        // data line: not empty ("\n", "\r\n", a lone "\r" at the end of the file), not a '#' line
+        const bool empty = c0 == '\n' || (c0 == '\r' && (p + 1 >= size || m[p + 1] == '\n'));
+        if (!empty && c0 != '#')
+            ++count;
+        const char *nl = (const char *)memchr(m + p, '\n', (size_t)(size - p));
+        if (!nl)
+            break;
+        p = (int64_t)(nl - m) + 1;
+    }
+    munmap((void *)m, (size_t)size);
     *n_lines = count;
     return SONICS_OK;
 }

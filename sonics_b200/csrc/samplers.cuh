@@ -73,11 +73,12 @@ __device__ __forceinline__ float floor_small(float x) { return __fadd_rd(x, 1258
 // the same pieces in lockstep form and are what the exact-pmf tests exercise.
 //
 // A lane has at most one draw in flight, so the three samplers share one register block:
-//   BTRS      fn p npq a b vr alpha ci cf fm | fk = candidate, A = ln of the scaled uniform
+//   BTRS      fn p a b vr alpha ci cf fm, squeeze: sL sQ sC3 sC4 sR5 dmax | fk = candidate, A = ln of the scaled uniform
 //   inversion a = (n+1) p/q, b = p/q         | fk = u (remaining uniform), A = px, ix = x, icap = cap
 //   PTRS      fn = lam (the reference's fp32 `hit`), a b vr, alpha = 1/alpha | ix = candidate
 struct DrawState {
-    float fn, p, npq, a, b, vr, alpha, ci, cf, fm, fk, A;
+    float fn, p, a, b, vr, alpha, ci, cf, fm, fk, A;
+    float sL, sQ, sC3, sC4, sR5, dmax; // BTRS squeeze (btrs_setup)
     int ix, icap;
 };
 
@@ -113,6 +114,19 @@ __device__ __forceinline__ void inv_run(DrawState &v, const float *rcp_tab)
     v.ix = (int)((r - base) >> 2);
 }
 // ---- BTRS: Binomial(n, p), p <= 0.5, n*p >= 10 ----
+// c0 = ln(p b0 / (q a0)) = log1p((frac - q) / (q a0)), frac = (n+1) p - m, as 2 atanh(w), w = eps / (2 + eps)
+// (|eps| <= 1/(q a0) <= 0.18 for n p >= 10: five terms reach fp32 accuracy)
+__device__ __forceinline__ float btrs_c0(float frac, float q, float a0)
+{
+    const float eps = __fmul_rn(frac - q, rcp_fast(__fmul_rn(q, a0)));
+    const float w = __fmul_rn(eps, rcp_fast(2.0f + eps));
+    const float w2 = __fmul_rn(w, w);
+    float c0 = fmaf(w2, 0.11111111f, 0.14285714f);
+    c0 = fmaf(c0, w2, 0.2f);
+    c0 = fmaf(c0, w2, 0.33333333f);
+    c0 = fmaf(c0, w2, 1.0f);
+    return __fmul_rn(__fmul_rn(2.0f, w), c0);
+}
 __device__ __forceinline__ void btrs_setup(DrawState &s, int n, float p)
 {
     s.fn = (float)n;
@@ -121,8 +135,7 @@ __device__ __forceinline__ void btrs_setup(DrawState &s, int n, float p)
     // n*p exactly as hi + lo (n < 2^24, so fma recovers the rounding error of the product)
     const float hi = s.fn * p;
     const float lo = fmaf(s.fn, p, -hi);
-    s.npq = hi * q;
-    const float spq = sqrt_fast(s.npq);
+    const float spq = sqrt_fast(hi * q);
     s.b = fmaf(2.53f, spq, 1.15f);
     const float rb = rcp_fast(s.b);
     s.a = fmaf(0.01f, p, fmaf(0.0248f, s.b, -0.0873f));
@@ -130,7 +143,33 @@ __device__ __forceinline__ void btrs_setup(DrawState &s, int n, float p)
     s.alpha = fmaf(5.1f, rb, 2.83f) * spq;
     s.ci = floorf(hi);                        // integer part of n*p (exact in fp32)
     s.cf = (hi - s.ci) + lo + 0.5f;           // c = n*p + 0.5 = ci + cf
-    s.fm = s.ci + floorf(s.cf - 0.5f + p);    // m = floor((n+1) p)
+    const float tf = s.cf - 0.5f + p;
+    const float fl = floorf(tf);
+    s.fm = s.ci + fl;                         // m = floor((n+1) p)
+    // ---- squeeze: ln f(k)/f(m) as a quartic in d = k - m with a rigorous remainder ----
+    // With a0 = m+1, b0 = n-m+1, ra = 1/a0, rb = 1/b0 the deviance form of btrs_full() expands to
+    //   ln f(k)/f(m) = L d - Q d^2 + C3 d^3 + C4 d^4 + R,   |R| <= 0.11 |d|^5 (ra^4 + rb^4)  for |d| <= 0.9 min(a0, b0)
+    //   L  = (ra - rb)/2 + c0 + (ra^2 - rb^2)/12            c0 = ln(p b0 / (q a0)), see btrs_full()
+    //   Q  = (ra + rb)/2 + (ra^2 + rb^2)/4 + (ra^3 + rb^3)/12
+    //   C3 = (ra^2 - rb^2)/6 + (ra^3 - rb^3)/6 + (ra^4 - rb^4)/12
+    //   C4 = -(ra^3 + rb^3)/12 - (ra^4 + rb^4)/8
+    // (-g(a;a0) - g(b;b0), ln(ab/(a0 b0))/2 and the Stirling tails, each expanded in d/a0 and d/b0; the remainder
+    // constant is checked against the exact log-pmf ratio for 10 <= np, n <= 5e6 in tests/test_sampler_math.py,
+    // worst observed 0.11 -> 0.25 used).  BTPE's squeeze (K&S step 5.2) is second order: its band ~|d|/(2npq) left
+    // 5 % of the trials undecided at npq = 1000 and 37 % at npq = 10; this one 0.2 % and 7 %, so the ~140-instruction
+    // exact test, which a warp executes for its 1-3 undecided lanes, runs in few of the rounds instead of most.
+    const float a0 = s.fm + 1.0f, b0 = s.fn - s.fm + 1.0f;
+    const float ra = rcp_fast(a0), rbb = rcp_fast(b0);
+    const float ra2 = __fmul_rn(ra, ra), rb2 = __fmul_rn(rbb, rbb);
+    const float ra3 = __fmul_rn(ra2, ra), rb3 = __fmul_rn(rb2, rbb);
+    const float ra4 = __fmul_rn(ra2, ra2), rb4 = __fmul_rn(rb2, rb2);
+    const float c0 = btrs_c0(tf - fl, q, a0);
+    s.sL = fmaf(0.083333333f, ra2 - rb2, fmaf(0.5f, ra - rbb, c0));
+    s.sQ = fmaf(0.083333333f, ra3 + rb3, fmaf(0.25f, ra2 + rb2, __fmul_rn(0.5f, ra + rbb)));
+    s.sC3 = fmaf(0.083333333f, ra4 - rb4, __fmul_rn(0.16666667f, (ra2 - rb2) + (ra3 - rb3)));
+    s.sC4 = fmaf(-0.125f, ra4 + rb4, __fmul_rn(-0.083333333f, ra3 + rb3));
+    s.sR5 = __fmul_rn(0.25f, ra4 + rb4);
+    s.dmax = floorf(__fmul_rn(0.9f, fminf(a0, b0)));
 }
 
 // One rejection trial.  0 = rejected, 1 = accepted (result s.fk), 2 = undecided: s.fk / s.A hold the
@@ -148,38 +187,70 @@ __device__ __forceinline__ int btrs_trial(DrawState &s, uint32_t bits_a, uint32_
     if (!(s.fk >= 0.0f && s.fk <= s.fn))
         return 0;
     s.A = log_fast(v * s.alpha * rcp_fast(fmaf(s.a * rus, rus, s.b)));
+    // quartic squeeze (btrs_setup).  Beyond dmax the pmf is below its value at m +- dmax (unimodal), so the upper
+    // bound at the clamped distance still rejects; acceptance needs the candidate in range.
     const float d = s.fk - s.fm;
-    const float ad = fabsf(d);
-    if (ad < fmaf(0.5f, s.npq, -1.0f)) {
-        // BTPE step 5.2: t - rho <= ln f(k)/f(m) <= t + rho
-        const float rn = rcp_fast(s.npq);
-        const float t = __fmul_rn(-0.5f * d * d, rn);
-        const float rho = __fmul_rn(ad * rn, fmaf(fmaf(ad, fmaf(ad, 0.33333333f, 0.625f), 0.16666667f), rn, 0.5f));
-        const float eps = fmaf(1e-5f, fabsf(t), 1e-5f); // margin for the fp32 evaluation of A, t and rho
-        if (s.A < t - rho - eps)
-            return 1;
-        if (s.A > t + rho + eps)
-            return 0;
-    }
+    const float dc = fminf(fmaxf(d, -s.dmax), s.dmax);
+    const float t = __fmul_rn(dc, fmaf(dc, fmaf(dc, fmaf(dc, s.sC4, s.sC3), -s.sQ), s.sL));
+    const float d2 = __fmul_rn(dc, dc);
+    const float rho = __fmul_rn(__fmul_rn(__fmul_rn(d2, d2), fabsf(dc)), s.sR5);
+    const float eps = fmaf(1e-5f, fabsf(t), 1e-5f); // margin for the fp32 evaluation of A, t and rho
+    if (s.A > __fadd_rn(__fadd_rn(t, rho), eps))
+        return 0;
+    if (d == dc && s.A < __fsub_rn(__fsub_rn(t, rho), eps))
+        return 1;
     return 2;
 }
 
-// The exact test for an undecided candidate: A <= ln f(k)/f(m), every term conditioned through
-// log1p so that each is O(|k-m|) (relative error 1e-7 per term => acceptance error <= ~2e-4 in the
-// far tail, on the ~2 % of trials that get here).
+// The exact test for an undecided candidate: A <= ln f(k)/f(m).
+//
+// With a = k+1, b = n-k+1, a0 = m+1, b0 = n-m+1, d = k-m and Stirling's series in Hoermann's (k+1) form,
+//   ln f(k)/f(m) = -g(a; a0) - g(b; b0) + 1/2 ln(a b / (a0 b0)) + d c0 + fc(m) + fc(n-m) - fc(k) - fc(n-k)
+//   g(x; x0) = x ln(x/x0) - (x - x0)               the deviance term, O(d^2 / x0) instead of O(d)
+//   c0       = ln(p b0 / (q a0)) = log1p((frac - q) / (q a0)),  frac = (n+1) p - m      a per-draw constant
+// (the saddle-point arrangement of Loader, "Fast and accurate computation of binomial probabilities", 2000).  The
+// textbook form sums three O(d) logarithm terms that cancel to O(d^2/npq): in fp32 it is off by up to 3e-3 at
+// n = 5e6 and needs two log1pf and one logf (~350 instructions executed by the 2-3 lanes of a warp that are
+// undecided).  Here every term is small by itself: g through x ln(x/x0) = 2 x atanh(v), v = d / (x + x0), as the
+// series d v + 2 x (v^3/3 + v^5/5 + ...), c0 the same way; |error| <= ~1e-5 for n up to 5e6 (CPU test in
+// tests/test_sampler_math.py), ~90 instructions without a slow-path call.  Candidates with |v| > 1/2 (k + 1 beyond
+// 3 (m + 1) or below (m + 1) / 3: far tails of the smallest means) take the logarithm directly.
+__device__ __forceinline__ float atanh_tail(float v) // v^3/3 + v^5/5 + ... + v^19/19
+{
+    const float v2 = __fmul_rn(v, v);
+    float s = 0.052631579f;
+    s = fmaf(s, v2, 0.058823529f);
+    s = fmaf(s, v2, 0.066666667f);
+    s = fmaf(s, v2, 0.076923077f);
+    s = fmaf(s, v2, 0.090909091f);
+    s = fmaf(s, v2, 0.11111111f);
+    s = fmaf(s, v2, 0.14285714f);
+    s = fmaf(s, v2, 0.2f);
+    s = fmaf(s, v2, 0.33333333f);
+    return __fmul_rn(__fmul_rn(s, v2), v);
+}
+// g(x; x0) = x ln(x / x0) - dx,  dx = x - x0
+__device__ __forceinline__ float deviance_term(float x, float x0, float dx)
+{
+    const float v = __fmul_rn(dx, rcp_fast(x + x0));
+    if (fabsf(v) > 0.5f)
+        return fmaf(x, logf(__fdiv_rn(x, x0)), -dx);
+    return fmaf(__fmul_rn(2.0f, x), atanh_tail(v), __fmul_rn(dx, v));
+}
 __device__ __forceinline__ bool btrs_full(const DrawState &s)
 {
     const float q = 1.0f - s.p;
-    const float r = s.p * rcp_fast(q);
     const float d = s.fk - s.fm;
-    const float nk = s.fn - s.fk + 1.0f;
-    const float k1 = s.fk + 1.0f;
-    const float rk1 = rcp_fast(k1), rnk = rcp_fast(nk); // IEEE divisions cost ~10 instructions each here
-    const float t1 = __fmul_rn(s.fm + 0.5f, log1pf(__fmul_rn(-d, rk1)));
-    const float t2 = __fmul_rn(s.fn - s.fm + 0.5f, log1pf(__fmul_rn(d, rnk)));
-    const float t3 = __fmul_rn(d, logf(__fmul_rn(r * nk, rk1)));
+    const float a0 = s.fm + 1.0f, b0 = s.fn - s.fm + 1.0f;
+    const float a = s.fk + 1.0f, b = s.fn - s.fk + 1.0f;
+    const float ga = deviance_term(a, a0, d);
+    const float gb = deviance_term(b, b0, -d);
+    const float lg = __fmul_rn(0.5f, log_fast(__fmul_rn(__fmul_rn(a, rcp_fast(a0)), __fmul_rn(b, rcp_fast(b0)))));
+    // c0: frac = (n+1) p - m from the split product of btrs_setup (cf = frac(n p) + 1/2, fm - ci = floor(...))
+    const float c0 = btrs_c0((s.cf - 0.5f + s.p) - (s.fm - s.ci), q, a0);
     // products and sums rounded one by one, in this order (no contraction: see the header note)
-    float h = __fadd_rn(__fadd_rn(t1, t2), t3);
+    float h = __fsub_rn(lg, __fadd_rn(ga, gb));
+    h = fmaf(d, c0, h);
     h = __fadd_rn(h, stirling_tail(s.fm));
     h = __fadd_rn(h, stirling_tail(s.fn - s.fm));
     h = __fsub_rn(h, stirling_tail(s.fk));

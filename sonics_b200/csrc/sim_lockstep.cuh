@@ -98,6 +98,8 @@ __device__ __forceinline__ int binomial_ls(PairRng &rng, int n, float p, const f
     if (__any_sync(SONICS_FULL, pend)) {
         if (pend)
             btrs_setup(ds, n, pp);
+        // The exact test of an undecided candidate runs inside the round (deferring it to a common point was
+        // measured: fewer executions, but the lanes it sends back retry alone -- 7.85e7 vs 8.46e7 reactions/s).
         do {
             if (pend) {
                 const uint2 w = rng.pair();
@@ -318,9 +320,24 @@ __global__ void __launch_bounds__(128, SONICS_LS_MIN_BLOCKS) k_pcr_ls(const SimA
                         n0 = ct > 0 ? ct : 0; // below the floor: the stale ct (:478)
                     }
                 }
-                const int x0 = binomial_ls(rng, n0, eff, rcp_tab);                 // mol_amp   (:454 / :478)
-                const int x1 = binomial_ls(rng, stutter ? x0 : 0, p_slip, rcp_tab); // mol_slip  (:458)
-                const int x2 = binomial_ls(rng, x1, p_upn, rcp_tab);                // mol_up    (:462)
+                // mol_amp (:454 / :478), mol_slip (:458), mol_up (:462): ONE copy of the sampler code in the loop --
+                // three inlined copies made the sweep ~55 KB of SASS and the warps waited on instruction fetch
+                // (ncu: stalled_no_instruction 2.8 per issue, issue-active 60 %)
+                int x0 = 0, x1 = 0, x2 = 0;
+#pragma unroll 1
+                for (int stage = 0; stage < 3; ++stage) {
+                    const int dn = stage == 0 ? n0 : (stage == 1 ? (stutter ? x0 : 0) : x1);
+                    const float dp = stage == 0 ? eff : (stage == 1 ? p_slip : p_upn);
+                    if (!__any_sync(SONICS_FULL, dn > 0))
+                        break; // nothing amplified / slipped in any lane: the later stages draw from 0
+                    const int x = binomial_ls(rng, dn, dp, rcp_tab);
+                    if (stage == 0)
+                        x0 = x;
+                    else if (stage == 1)
+                        x1 = x;
+                    else
+                        x2 = x;
+                }
                 if (in) {
                     cur += x0 - x1;              // products[al] += mol_amp - mol_slip (:466)
                     const int down = x1 - x2;    // mol_down

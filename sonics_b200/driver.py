@@ -264,25 +264,28 @@ PIECE_BYTES = 8 << 20  # VCF bytes per pipeline piece (~140 k genotypes of a 32-
 
 
 def vcf_pipeline(feed_in, byte_range, line_base, out_path, header, constants, options, seed, compute,
-                 piece_bytes=None):
+                 piece_bytes=None, pieces=None, line_bases=None):
     """One process's share of VCF mode, pipelined: the file range is cut into pieces; while the GPU runs
     piece k (`compute`, a blocking native call that releases the GIL), one host thread parses piece k+1
     (sonics_vcf_parse_range) and another appends the rows of piece k-1 to out_path (sonics_rows_write_part).
 
     A genotype's RNG key is its cell in the (data line x sample) grid of the whole file: line_base = data
     lines before byte_range (hostio.lines_before), then every piece adds the lines it parsed -- so neither
-    the pieces nor the ranks change the output.  Returns (rows, simulated genotypes, timings dict)."""
+    the pieces nor the ranks change the output.  With `pieces` (explicit [begin, end) list, not necessarily
+    adjacent: the share of one rank of a multi-GPU run) every piece brings its own line base in `line_bases`.
+    Returns (rows, simulated genotypes, timings dict); timings["row_bytes"] = bytes written per piece."""
     from concurrent.futures import ThreadPoolExecutor
     from . import hostio
-    lo, hi = byte_range
-    end = os.path.getsize(feed_in) if hi < 0 else hi
-    # pieces small enough that the un-overlapped first parse and last write are a small share of the range
-    piece_bytes = piece_bytes or max(1 << 20, min(PIECE_BYTES, (end - lo) // 8))
-    cuts = list(range(lo, end, piece_bytes)) + [end]
-    pieces = [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1)]
-    if pieces and hi < 0:
-        pieces[-1] = (pieces[-1][0], -1)
-    tm = {"ingest": 0.0, "simulate": 0.0, "write": 0.0, "pieces": len(pieces)}
+    if pieces is None:
+        lo, hi = byte_range
+        end = os.path.getsize(feed_in) if hi < 0 else hi
+        # pieces small enough that the un-overlapped first parse and last write are a small share of the range
+        piece_bytes = piece_bytes or max(1 << 20, min(PIECE_BYTES, (end - lo) // 8))
+        cuts = list(range(lo, end, piece_bytes)) + [end]
+        pieces = [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1)]
+        if pieces and hi < 0:
+            pieces[-1] = (pieces[-1][0], -1)
+    tm = {"ingest": 0.0, "simulate": 0.0, "write": 0.0, "pieces": len(pieces), "row_bytes": []}
     n_rows = n_sim = 0
 
     def parse(rng):
@@ -293,9 +296,11 @@ def vcf_pipeline(feed_in, byte_range, line_base, out_path, header, constants, op
 
     def write(v, verdicts, first):
         t = time.time()
+        before = 0 if first else os.path.getsize(out_path)
         hostio.write_rows(out_path, verdicts, v, options["monte_carlo"], options["add_ratios"], options["name"],
                           options["block"], header=header and first, append=not first)
         v.close()
+        tm["row_bytes"].append(os.path.getsize(out_path) - before)
         return time.time() - t
 
     if not pieces:
@@ -310,6 +315,8 @@ def vcf_pipeline(feed_in, byte_range, line_base, out_path, header, constants, op
             tm["ingest"] += tp
             if k + 1 < len(pieces):
                 nxt = parser.submit(parse, pieces[k + 1])
+            if line_bases is not None:
+                line_base = line_bases[k]
             uids = v.uids(line_base)
             line_base += v.n_blocks
             n_rows += v.n_rows
@@ -393,10 +400,13 @@ def _run_vcf_ranks(feed_in, constants, ranges, options, seed, chunk, out_file_pa
                    piece_bytes=None):
     """VCF mode under torchrun, one process per GPU: the ranks share ingest, simulation and output.
 
-    Rank r runs vcf_pipeline() on its byte range of the file (hostio.byte_ranges; the number of data lines
-    before the range comes from a newline scan, so no rank waits for another) and writes <out>.part<r>; at the
-    end one all_gather of part sizes gives every rank its offset in the output file and each rank copies its
-    own part there.  No collective touches the data path.  `compute` replaces the GPU call in the CPU (gloo) test."""
+    The file is cut into byte pieces dealt round-robin (piece k -> rank k mod world: genotypes that need 100 or
+    1000 simulations cluster by locus, so interleaving evens the load where contiguous shares did not).  Every
+    rank counts the data lines of its own pieces (a memchr scan) and one all_gather of those counts gives every
+    piece its line base -- the RNG key of a genotype stays its cell in the (data line x sample) grid of the whole
+    file.  Rank r runs vcf_pipeline() over its pieces into <out>.part<r>; a second all_gather (bytes written per
+    piece) gives every piece its offset in the output file and each rank copies its own pieces there.  No
+    collective touches the data path.  `compute` replaces the GPU call in the CPU (gloo) test."""
     import torch.distributed as dist
     from . import hostio
     if not dist.is_initialized():
@@ -411,31 +421,50 @@ def _run_vcf_ranks(feed_in, constants, ranges, options, seed, chunk, out_file_pa
     local = int(os.environ.get("LOCAL_RANK", rank))
     compute = compute or (lambda off, al, rd, nz, uids: run_batch_verdicts(
         off, al, rd, nz, constants, ranges, options, seed, local, chunk, uids))
-    rng = hostio.byte_ranges(feed_in, world)[rank]
-    line_base = hostio.lines_before(feed_in, rng[0]) if rng[0] > 0 else 0
-    n_rows, n_sim, tm = vcf_pipeline(feed_in, rng, line_base, "%s.part%d" % (out_file_path, rank), rank == 0,
-                                     constants, options, seed, compute, piece_bytes)
-    t1 = time.time()
-    # join: every rank copies its own part to its offset of the output file (parallel; rank 0 sizes the file)
+    size = os.path.getsize(feed_in)
+    piece_bytes = piece_bytes or max(1 << 20, min(PIECE_BYTES, size // (8 * world)))
+    all_pieces = hostio.pieces_of(feed_in, piece_bytes)
+    mine = list(range(rank, len(all_pieces), world))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, [hostio.count_lines(feed_in, *all_pieces[i]) for i in mine])
+    n_lines = [0] * len(all_pieces)
+    for r in range(world):
+        for j, i in enumerate(range(r, len(all_pieces), world)):
+            n_lines[i] = gathered[r][j]
+    bases = np.concatenate([[0], np.cumsum(n_lines)]).astype(np.int64)
     part = "%s.part%d" % (out_file_path, rank)
-    counts = [None] * world
-    dist.all_gather_object(counts, (n_rows, os.path.getsize(part)))
+    n_rows, n_sim, tm = vcf_pipeline(feed_in, None, 0, part, rank == 0, constants, options, seed, compute,
+                                     pieces=[all_pieces[i] for i in mine], line_bases=[int(bases[i]) for i in mine])
+    t1 = time.time()
+    # join: every rank copies its pieces to their offsets of the output file (parallel; rank 0 sizes the file)
+    dist.all_gather_object(gathered, (n_rows, tm["row_bytes"] if mine else [os.path.getsize(part)]))
+    sizes = [0] * max(1, len(all_pieces))
+    for r in range(world):
+        for j, i in enumerate(range(r, len(all_pieces), world)):
+            sizes[i] = gathered[r][1][j]
+    if not all_pieces:
+        sizes = [gathered[0][1][0]]  # header only, written by rank 0
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     if rank == 0:
         with open(out_file_path, "wb") as f:
-            f.truncate(sum(c[1] for c in counts))
+            f.truncate(int(offs[-1]))
     dist.barrier()
     with open(out_file_path, "r+b") as fo, open(part, "rb") as fi:
-        fo.seek(sum(c[1] for c in counts[:rank]))
-        while True:
-            buf = fi.read(8 << 20)
-            if not buf:
-                break
-            fo.write(buf)
+        for j, i in enumerate(mine if all_pieces else ([0] if rank == 0 else [])):
+            fo.seek(int(offs[i]))
+            left = sizes[i]
+            while left > 0:
+                buf = fi.read(min(left, 8 << 20))
+                if not buf:
+                    break
+                fo.write(buf)
+                left -= len(buf)
     os.unlink(part)
     dist.barrier()
     LAST_TIMINGS.clear()
-    LAST_TIMINGS.update(tm, join=time.time() - t1, genotypes=n_sim, wall=time.time() - t0)
-    if sum(c[0] for c in counts) == 0:
+    tm.pop("row_bytes", None)
+    LAST_TIMINGS.update(tm, join=time.time() - t1, genotypes=n_sim, wall=time.time() - t0, pieces_total=len(all_pieces))
+    if sum(g[0] for g in gathered) == 0:
         raise Exception("No valid genotype after parsing VCF file.")
 
 

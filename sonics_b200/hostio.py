@@ -63,6 +63,25 @@ def lines_before(path, byte_end):
     return n.value
 
 
+def count_lines(path, byte_begin, byte_end):
+    """Data lines whose first byte lies in [byte_begin, byte_end) (byte_end < 0: end of file): the blocks a
+    Vcf(byte_range=(byte_begin, byte_end)) parse yields."""
+    n = ctypes.c_int64(0)
+    check(_abi.load().sonics_vcf_count_lines(str(path).encode(), int(byte_begin), int(byte_end), ctypes.byref(n)))
+    return n.value
+
+
+def pieces_of(path, piece_bytes):
+    """[begin, end) byte pieces that tile the file (the last one ends at -1 = end of file)."""
+    import os
+    size = os.path.getsize(path)
+    cuts = list(range(0, size, max(1, int(piece_bytes)))) + [size]
+    out = [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1)]
+    if out:
+        out[-1] = (out[-1][0], -1)
+    return out
+
+
 def write_rows(path, verdicts, vcf=None, monte_carlo=False, add_ratios="", name="sample", block="Block", header=True,
                append=False):
     """Header + rows of run_sonics() (sonics:174-207, :437); verdicts: structured array (VERDICT_DTYPE).

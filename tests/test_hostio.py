@@ -173,11 +173,18 @@ def test_byte_range_tilings_parse_every_line_once(tmp_path, strict):
         assert _join([_csr(a), _csr(b)]) == ref, c
         # the newline scan counts exactly the data lines the parser assigns to [0, c) ...
         assert hostio.lines_before(p, c) == a.n_blocks, c
+        # ... and so does the per-range count the ranks of a multi-GPU run exchange (memchr scan of the range only)
+        assert hostio.count_lines(p, 0, c) == a.n_blocks and hostio.count_lines(p, c, -1) == b.n_blocks, c
         # ... so the RNG keys (cells of the line x sample grid) of a range do not depend on the cut
         assert list(a.uids(0)) + list(b.uids(a.n_blocks)) == list(whole.uids(0)), c
     for world in (3, 4, 8, 64):
         parts = [_csr(hostio.Vcf(p, strict, seed=77, byte_range=r)) for r in hostio.byte_ranges(p, world)]
         assert _join(parts) == ref, world
+    for piece in (17, 64, 301, size, size + 5):  # the round-robin pieces of _run_vcf_ranks
+        pcs = hostio.pieces_of(p, piece)
+        vs = [hostio.Vcf(p, strict, seed=77, byte_range=r) for r in pcs]
+        assert _join([_csr(v) for v in vs]) == ref, piece
+        assert [hostio.count_lines(p, *r) for r in pcs] == [v.n_blocks for v in vs], piece
 
 
 def test_part_files_concatenate_to_the_whole_output(tmp_path):
