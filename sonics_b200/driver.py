@@ -356,6 +356,7 @@ def run_sonics(feed_in, constants, ranges, options, seed=None, gpus=1, chunk=655
             lambda off, al, rd, nz, uids: run_batch_verdicts(off, al, rd, nz, constants, ranges, options, seed, 0,
                                                              chunk, uids))
         LAST_TIMINGS.clear()
+        tm.pop("row_bytes", None)
         LAST_TIMINGS.update(tm, join=0.0, genotypes=n_sim, wall=time.time() - t0)
         if n_rows == 0:
             raise Exception("No valid genotype after parsing VCF file.")

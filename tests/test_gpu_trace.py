@@ -77,6 +77,7 @@ def replay_all(genotypes, noise, n_sims, seed, **kw):
 
 def test_replay_default_configs():
     n, dp, dlam, kinds = replay_all([CFG1, CFG2, "3|40;4|25;7|2"], [0.0, 0.0, 0.0], 96, seed=20261019)
+    print("default configs: %d draws, worst relative dp %.3g" % (n, dp))
     assert n > 96 * 3 * 300 and kinds == {1, 2}
     # p of the slip draws: fp32 incremental expm1 on the device vs fp64 pow in the reference
     assert dp < 2e-5, dp
@@ -90,6 +91,7 @@ def test_replay_noise_and_wide_window():
     nc = float(np.float32(orc.auto_noise_coef(rd)))
     assert nc > 0
     n, dp, dlam, kinds = replay_all([CFG3], [nc], 48, seed=7, n_cycles=30, capture_cycle=16)
+    print("cfg3: %d draws, worst relative dp %.3g" % (n, dp))
     assert n > 48 * 2000 and dlam == 0.0 and dp < 5e-5, (n, dp, dlam)
 
 
@@ -102,6 +104,7 @@ def test_replay_noise_and_wide_window():
                                 dict(down=(0, 0.5), up=(0, 0.5)), dict(capture=(-1.9, -1.5))])
 def test_replay_option_matrix(kw):
     n, dp, dlam, kinds = replay_all([CFG1, "8|50;9|3;14|20", "2|9;3|1"], [0.0, 0.004, 0.0], 64, seed=11, **kw)
+    print("option matrix %s: %d draws, worst relative dp %.3g" % (kw, n, dp))
     assert n > 0 and dlam == 0.0 and dp < 1e-4, (n, dp, dlam)
 
 
