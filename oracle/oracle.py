@@ -111,6 +111,11 @@ def lib():
         L.oracle_one_repeat.restype = ctypes.c_int
         L.oracle_one_repeat.argtypes = [ctypes.c_void_p, ctypes.POINTER(OracleCfg), ctypes.c_void_p, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.c_void_p]
+        L.oracle_replay_script_where.restype = ctypes.c_int
+        L.oracle_replay_script_where.argtypes = [ctypes.POINTER(OracleCfg), ctypes.c_void_p, ctypes.c_int,
+                                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                                 ctypes.c_int64, ctypes.POINTER(ctypes.c_double),
+                                                 ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_double)]
         L.oracle_descriptors.restype = None
         L.oracle_descriptors.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                          ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
@@ -192,6 +197,20 @@ def replay_script(cfg, alleles, params4, start_idx, script):
                                     script.ctypes.data, int(script.shape[0]), rec.ctypes.data, pool.ctypes.data,
                                     ctypes.byref(used), ctypes.byref(dp), ctypes.byref(dlam), ctypes.byref(err_pos))
     return rc, rec[0], pool, used.value, dp.value, dlam.value, err_pos.value
+
+
+def replay_script_where(cfg, alleles, params4, start_idx, script):
+    """(max relative deviation of a binomial probability, index of that request, the reference's p there)."""
+    alleles = np.ascontiguousarray(alleles, dtype=np.int64)
+    params4 = np.ascontiguousarray(params4, dtype=np.float64)
+    start_idx = np.ascontiguousarray(start_idx, dtype=np.int64)
+    script = np.ascontiguousarray(script, dtype=SCRIPT_DTYPE)
+    dp, pos, pref = ctypes.c_double(0), ctypes.c_int64(0), ctypes.c_double(0)
+    lib().oracle_replay_script_where(ctypes.byref(cfg), alleles.ctypes.data, int(alleles.shape[0]),
+                                     params4.ctypes.data, start_idx.ctypes.data, int(start_idx.shape[0]),
+                                     script.ctypes.data, int(script.shape[0]), ctypes.byref(dp), ctypes.byref(pos),
+                                     ctypes.byref(pref))
+    return dp.value, pos.value, pref.value
 
 
 def record_script(cfg, alleles, seed, cap=1 << 16):

@@ -52,10 +52,29 @@ BINOM_CASES = [(1, 0.3), (5, 0.5), (20, 0.3), (100, 0.05), (1000, 0.005), (30000
                (1200000, 0.0123), (3000000, 0.1), (7503, 0.9991), (37, 0.4999), (1000000, 0.5)]
 
 
-@pytest.mark.parametrize("n,p", BINOM_CASES)
+def _k1_request_mix():
+    """Ten (n, p) requests taken from what K1 actually asks for: the draws of oracle-recorded cfg2 / cfg3
+    simulations, at the deciles of n * min(p, 1-p) over the requests with n p >= 1."""
+    from oracle import oracle as orc
+    from tests.util import CFG2, CFG3
+    req = []
+    for gt, kw, seeds in ((CFG2, {}, range(6)), (CFG3, dict(n_cycles=30, capture_cycle=16), range(2))):
+        reads = orc.parse_reads(gt)
+        for sd in seeds:
+            _, _, script = orc.record_script(orc.make_cfg(rng_mode=1, with_readout=False, **kw), reads, 4242 + sd)
+            b = script[script["kind"] == 1]
+            req += [(int(n), float(p)) for n, p in zip(b["n"], b["p"])]
+    req = sorted(set(r for r in req if r[0] * min(r[1], 1 - r[1]) >= 1.0), key=lambda r: r[0] * min(r[1], 1 - r[1]))
+    return [req[int(q * (len(req) - 1))] for q in np.linspace(0.02, 0.98, 10)]
+
+
+K1_MIX = _k1_request_mix()
+
+
+@pytest.mark.parametrize("n,p", BINOM_CASES + K1_MIX)
 def test_binomial_sampler_matches_exact_pmf(n, p):
     e = engine()
-    N = 2_000_000
+    N = 20_000_000
     x = e.debug_sample("binomial", n, p, N, seed=1234 + n)
     p32 = float(np.float32(p))  # the kernel receives p as a float
     assert x.min() >= 0 and x.max() <= n
@@ -81,7 +100,7 @@ def test_binomial_sampler_matches_exact_pmf(n, p):
 @pytest.mark.parametrize("lam", [0.3, 3.0, 9.9, 10.0, 17.5, 250.0, 41234.5, 1.5e6])
 def test_poisson_sampler_matches_exact_pmf(lam):
     e = engine()
-    N = 2_000_000
+    N = 20_000_000
     x = e.debug_sample("poisson", 0, lam, N, seed=77)
     sd = np.sqrt(lam)
     assert abs(x.mean() - lam) < 5 * sd / np.sqrt(N)

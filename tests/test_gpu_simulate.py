@@ -17,7 +17,9 @@ from tests.util import CFG1, CFG2, CFG3
 
 pytestmark = pytest.mark.gpu
 
-N_ORACLE = int(os.environ.get("SONICS_KS_ORACLE", "100000" if (os.cpu_count() or 1) >= 16 else "30000"))
+# north star: two-sample KS p > 0.01 at >= 1e5 simulations -- literally: 1e5 oracle simulations per group on any
+# box (the C oracle needs 0.12 ms per cfg2 simulation, 0.5 ms per cfg3 simulation, spread over the host cores)
+N_ORACLE = max(100000, int(os.environ.get("SONICS_KS_ORACLE", "100000")))
 
 
 def test_determinism_and_split_invariance():
@@ -85,11 +87,11 @@ def _compare(genotype, noise_coef, n_gpu, seed, okw, pkw, groups=None):
         report.append((lbl, len(g), len(o), sg, so, z, ks_all.pvalue, ks_valid.pvalue if ks_valid else float("nan")))
     for r in report:
         print("group %-6s n_gpu=%d n_oracle=%d sentinel gpu=%.4f oracle=%.4f z=%+.2f KS(all) p=%.3f KS(valid) p=%.3f" % r)
-    k = len(report)
     for lbl, ng, no, sg, so, z, p_all, p_valid in report:
+        assert ng >= 100000 and no >= 100000, (lbl, ng, no)
         assert abs(z) < 4.0, (lbl, sg, so, z)
-        assert p_all > 0.01 / k, (lbl, p_all)
-        assert not (p_valid < 0.01 / k), (lbl, p_valid)
+        assert p_all > 0.01, (lbl, p_all)              # the gate as the north star states it, per group
+        assert not (p_valid < 0.01), (lbl, p_valid)
 
 
 def test_ks_cfg1_readme_example():
@@ -97,14 +99,15 @@ def test_ks_cfg1_readme_example():
 
 
 def test_ks_cfg2_eight_alleles():
-    _compare(CFG2, 0.0, 1_600_000, 2, {}, {})
+    # BASELINE.json configs[1]: 1e6 simulations per genotype group on the device
+    _compare(CFG2, 0.0, 8_000_000, 2, {}, {})
 
 
 def test_ks_noise_and_capture_variants():
     gt = "9|1;10|54;11|914;12|15"
     nc = orc.auto_noise_coef(orc.parse_reads(gt))
     assert nc > 0
-    _compare(gt, nc, 400_000, 3, {}, {})
+    _compare(gt, nc, 480_000, 3, {}, {})
 
 
 def test_ks_nondefault_options():
@@ -117,16 +120,11 @@ def test_ks_nondefault_options():
 
 
 def test_ks_cfg3_wide_window():
+    # 40 input alleles, 30 cycles: >= 1e5 simulations per group on both sides for 8 of the 40 groups
     nc = orc.auto_noise_coef(orc.parse_reads(CFG3))
     okw = dict(n_cycles=30, capture_cycle=16)
     pkw = dict(n_cycles=30, capture_cycle=16)
-    global N_ORACLE
-    keep = N_ORACLE
-    N_ORACLE = max(4000, keep // 10)  # 1316 steps per reaction: keep the CPU side bounded
-    try:
-        _compare(CFG3, nc, 800_000, 5, okw, pkw, groups=[28, 36, 20, 45])
-    finally:
-        N_ORACLE = keep
+    _compare(CFG3, nc, 4_400_000, 5, okw, pkw, groups=[28, 36, 20, 45, 10, 24, 32, 40])
 
 
 def test_random_start_groups_and_less_than_two_alleles():

@@ -70,6 +70,11 @@ def replay_all(genotypes, noise, n_sims, seed, **kw):
             lnl = out["lnL"][g, j]
             assert lnl == rec["lnL"] or abs(lnl - rec["lnL"]) <= 1e-9 * abs(rec["lnL"]), (g, j, lnl, rec["lnL"])
             n_draws += n
+            if dp > worst_dp and dp > 1e-6:
+                _, pos, pref = orc.replay_script_where(cfg, rd, out["simpar"][g, j], idx, script)
+                print("   worst dp so far %.3g: genotype %d sim %d draw %d of %d: n=%d p_gpu=%.9g p_ref=%.9g "
+                      "(down=%.4g up=%.4g)" % (dp, g, j, pos, n, script["n"][pos], script["p"][pos], pref,
+                                               out["simpar"][g, j, 0], out["simpar"][g, j, 1]))
             worst_dp, worst_dlam = max(worst_dp, dp), max(worst_dlam, dlam)
             kinds |= set(np.unique(script["kind"]).tolist())
     return n_draws, worst_dp, worst_dlam, kinds
@@ -79,8 +84,9 @@ def test_replay_default_configs():
     n, dp, dlam, kinds = replay_all([CFG1, CFG2, "3|40;4|25;7|2"], [0.0, 0.0, 0.0], 96, seed=20261019)
     print("default configs: %d draws, worst relative dp %.3g" % (n, dp))
     assert n > 96 * 3 * 300 and kinds == {1, 2}
-    # p of the slip draws: fp32 incremental expm1 on the device vs fp64 pow in the reference
-    assert dp < 2e-5, dp
+    # p of the slip draws: fp32 incremental expm1 on the device vs fp64 pow in the reference.  Measured over all
+    # the cases of this file (r02): <= 2.9e-7 relative, i.e. a few fp32 ulps -- the recurrence does not drift
+    assert dp < 1e-6, dp
     # lam of the capture step: the same C-float arithmetic on both sides (sonics.pyx:414-419)
     assert dlam == 0.0, dlam
 
@@ -92,7 +98,7 @@ def test_replay_noise_and_wide_window():
     assert nc > 0
     n, dp, dlam, kinds = replay_all([CFG3], [nc], 48, seed=7, n_cycles=30, capture_cycle=16)
     print("cfg3: %d draws, worst relative dp %.3g" % (n, dp))
-    assert n > 48 * 2000 and dlam == 0.0 and dp < 5e-5, (n, dp, dlam)
+    assert n > 48 * 2000 and dlam == 0.0 and dp < 1e-6, (n, dp, dlam)
 
 
 @pytest.mark.parametrize("kw", [dict(floor=-1), dict(floor=0), dict(floor=-3), dict(floor=2),
@@ -105,7 +111,7 @@ def test_replay_noise_and_wide_window():
 def test_replay_option_matrix(kw):
     n, dp, dlam, kinds = replay_all([CFG1, "8|50;9|3;14|20", "2|9;3|1"], [0.0, 0.004, 0.0], 64, seed=11, **kw)
     print("option matrix %s: %d draws, worst relative dp %.3g" % (kw, n, dp))
-    assert n > 0 and dlam == 0.0 and dp < 1e-4, (n, dp, dlam)
+    assert n > 0 and dlam == 0.0 and dp < 1e-6, (n, dp, dlam)
 
 
 def test_counters_and_trace_hooks_are_independent():
