@@ -195,9 +195,13 @@ int sonics_evaluate(sonics_ctx *ctx, const SonicsParams *params, const void *dev
                     const int32_t *dev_active, int n_active, int64_t n_run, int64_t out_stride, const double *dev_lnL,
                     const uint16_t *dev_group, const double *dev_identity, const float *dev_rsq, int final_round,
                     SonicsVerdict *dev_verdict, void *dev_scratch, size_t dev_scratch_bytes, void *stream);
-/* Scratch sonics_evaluate needs when n_run > SONICS_STATS_MAX_REPS (CUB sort / scan path, one genotype
- * at a time); 0 below that, where dev_scratch may be NULL. */
+/* Scratch sonics_evaluate needs when n_run > SONICS_STATS_MAX_REPS or a genotype has more than 2048 start-allele
+ * groups (statistics over global memory: CUB sort, then the on-chip algorithm on global arrays; --monte_carlo: one
+ * genotype at a time); 0 otherwise, where dev_scratch may be NULL.  Size for one genotype = the minimum. */
 size_t sonics_stats_scratch_bytes(int64_t n_run, int max_alleles, int random_start);
+/* The same for n_active genotypes in one statistics launch (default mode: global-memory form of the on-chip
+ * kernel, 26 bytes per simulation; a smaller buffer, down to the one-genotype size, means several launches). */
+size_t sonics_stats_scratch_bytes_batch(int n_active, int64_t n_run, int max_alleles, int random_start);
 
 /* K4: replay simulation dev_verdict[g].best_sim of every listed genotype (same Philox stream, hence
  * the same PCR pool and lnL) with the sequencing readout switched on, and fill dev_verdict[g].identity
@@ -219,6 +223,9 @@ size_t sonics_genotype_work_bytes(int n_gt, int n_alleles_total, int max_reps);
 /* The same for one mode: the default mode needs no identity / r^2 planes (10 instead of 22 bytes per simulation).
  * A caller with many genotypes and a large -r picks its batch size from this (driver.run_batch_verdicts). */
 size_t sonics_genotype_work_bytes_mode(int n_gt, int n_alleles_total, int max_reps, int monte_carlo);
+/* ... and for the actual inputs of a call (knows the largest number of start-allele groups: --random with more
+ * than 45 alleles, or -r above SONICS_STATS_MAX_REPS, route the statistics through global memory). */
+size_t sonics_genotype_work_bytes_for(const SonicsParams *params, int n_gt, const int32_t *allele_off, int max_reps);
 int sonics_genotype_batch(sonics_ctx *ctx, const SonicsParams *params, int n_gt, const int32_t *allele_off,
                           const int32_t *allele, const int32_t *reads, const float *noise_coef, const uint32_t *uid,
                           int max_reps, uint64_t seed, SonicsVerdict *verdict_out, void *dev_work,

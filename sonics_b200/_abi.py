@@ -92,9 +92,11 @@ PROTOTYPES = {
     "sonics_evaluate": (_I, [_P, ctypes.POINTER(SonicsParams), _P, _I, _P, _I, _I64, _I64, _P, _P, _P, _P, _I, _P, _P,
                              _SZ, _P]),
     "sonics_stats_scratch_bytes": (_SZ, [_I64, _I, _I]),
+    "sonics_stats_scratch_bytes_batch": (_SZ, [_I, _I64, _I, _I]),
     "sonics_replay_best": (_I, [_P, ctypes.POINTER(SonicsParams), _P, _I, _P, _I, _U64, _P, _P, _SZ, _P]),
     "sonics_genotype_work_bytes": (_SZ, [_I, _I, _I]),
     "sonics_genotype_work_bytes_mode": (_SZ, [_I, _I, _I, _I]),
+    "sonics_genotype_work_bytes_for": (_SZ, [ctypes.POINTER(SonicsParams), _I, _P, _I]),
     "sonics_genotype_batch": (_I, [_P, ctypes.POINTER(SonicsParams), _I, _P, _P, _P, _P, _P, _I, _U64, _P, _P, _SZ,
                                    _P]),
     "sonics_debug_counters": (_I, [_P, _P]),

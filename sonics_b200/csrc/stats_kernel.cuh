@@ -23,6 +23,8 @@
 #pragma once
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/sonics_b200.h"
 #include "sim_kernel.cuh"
 
@@ -47,6 +49,16 @@ struct EvalArgs {
     double padjust, thr;
     double add_q[SONICS_MAX_ADD_RATIOS];
     SonicsVerdict *verdict;
+    // global-memory form (k_evaluate_t<true>): per-genotype arrays at stride n_run + 1, filled by the host path
+    // (abi_stats.inl: keys / indices sorted by CUB); slot_base = first active-list position of this launch
+    int32_t slot_base;
+    unsigned long long *g_key; // sorted lnL keys
+    uint32_t *g_idx;           // simulation index of the sorted element; reused as S_best
+    uint32_t *g_S;
+    uint32_t *g_thead, *g_tend;
+    uint16_t *g_slot;
+    int *g_cnt, *g_cnt_valid;  // per genotype x n_slots_cap, only when the groups do not fit shared memory
+    unsigned long long *g_maxk;
 };
 
 __device__ __forceinline__ unsigned long long f64_key(double v)
@@ -73,13 +85,14 @@ __device__ __forceinline__ double lerp_np(double a, double b, double t)
     return r;
 }
 
-struct StatsSmem {
+template <typename HT>
+struct StatsArrays {
     unsigned long long *key; // n_pad
     uint32_t *idx;           // n_pad   (simulation index; later reused as S_best, n_pad + 1 needs <= n_pad + pad)
     uint32_t *S;             // n_pad + 1
     uint16_t *slot;          // n_pad
-    uint16_t *thead;         // n_pad
-    uint16_t *tend;          // n_pad
+    HT *thead;               // n_pad   (u16 on chip: n <= 8192; u32 in global memory)
+    HT *tend;                // n_pad
     int *cnt;                // n_slots
     int *cnt_valid;          // n_slots
     unsigned long long *maxk; // n_slots
@@ -159,7 +172,8 @@ __device__ __forceinline__ void scan_slot(const uint16_t *slot, int target, int 
 }
 
 // k-th smallest (0-based) element of group `target`, given its scan S
-__device__ __forceinline__ void pick_order_stats(const StatsSmem &m, const uint32_t *S, int target, int n, int k0,
+template <typename HT>
+__device__ __forceinline__ void pick_order_stats(const StatsArrays<HT> &m, const uint32_t *S, int target, int n, int k0,
                                                  int k1, double *out /* smem[2] */)
 {
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -198,6 +212,72 @@ __device__ __forceinline__ void bitonic_sort(unsigned long long *key, uint32_t *
     }
 }
 
+// Tie blocks of a sorted key array in global memory: thead[i] = first index of the run of equal keys that holds i,
+// tend[i] = one past its last index.  A forward max-scan of the run heads and a backward min-scan of the run ends,
+// each thread owning a contiguous chunk (the sentinel block at the bottom can hold millions of elements, so the
+// per-run loop of the on-chip form would leave it to one thread).  wsum: 32 words of shared memory.
+__device__ __forceinline__ void tie_blocks_global(const unsigned long long *key, int n, uint32_t *thead, uint32_t *tend,
+                                                  uint32_t *wsum)
+{
+    const int T = blockDim.x, w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const int per = (n + T - 1) / T;
+    const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+    // forward: running maximum of the head positions
+    uint32_t run = 0;
+    for (int i = lo; i < hi; ++i)
+        if (i > 0 && key[i] != key[i - 1])
+            run = (uint32_t)i;
+    uint32_t inc = run;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (l >= o)
+            inc = max(inc, y);
+    }
+    __syncthreads();
+    if (l == 31)
+        wsum[w] = inc;
+    __syncthreads();
+    uint32_t carry = 0;
+    for (int k = 0; k < w; ++k)
+        carry = max(carry, wsum[k]);
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (l > 0)
+        carry = max(carry, prev);
+    for (int i = lo; i < hi; ++i) {
+        if (i > 0 && key[i] != key[i - 1])
+            carry = (uint32_t)i;
+        thead[i] = carry;
+    }
+    __syncthreads();
+    // backward: running minimum of the end positions
+    uint32_t rmin = (uint32_t)n;
+    for (int i = hi - 1; i >= lo; --i)
+        if (i + 1 < n && key[i + 1] != key[i])
+            rmin = (uint32_t)(i + 1);
+    uint32_t dec = rmin;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_down_sync(0xffffffffu, dec, o);
+        if (l + o < 32)
+            dec = min(dec, y);
+    }
+    __syncthreads();
+    if (l == 0)
+        wsum[w] = dec;
+    __syncthreads();
+    uint32_t cmin = (uint32_t)n;
+    for (int k = w + 1; k < (T >> 5); ++k)
+        cmin = min(cmin, wsum[k]);
+    const uint32_t nxt = __shfl_down_sync(0xffffffffu, dec, 1);
+    if (l < 31)
+        cmin = min(cmin, nxt);
+    for (int i = hi - 1; i >= lo; --i) {
+        if (i + 1 < n && key[i + 1] != key[i])
+            cmin = (uint32_t)(i + 1);
+        tend[i] = cmin;
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ int slot_of(int gid, int A, int first_idx, int random_start)
 {
     if (random_start)
@@ -206,40 +286,65 @@ __device__ __forceinline__ int slot_of(int gid, int A, int first_idx, int random
     return lo == first_idx ? hi : lo; // index of the randomly chosen second allele
 }
 
-__global__ void __launch_bounds__(SONICS_STATS_THREADS) k_evaluate(const EvalArgs a, int n_slots_cap)
+// BIG = false: everything in shared memory (n_run <= SONICS_STATS_MAX_N, groups <= SONICS_STATS_MAX_SLOTS), the sort
+//               included (bitonic).
+// BIG = true:  the per-simulation arrays live in global memory (EvalArgs::g_*), already sorted by CUB; the group
+//              counters stay in shared memory when they fit (smem_slots != 0).  Default mode only: the --monte_carlo
+//              branch needs two more sorts and keeps its own path (stats_big.cuh).
+template <bool BIG>
+__global__ void __launch_bounds__(BIG ? 1024 : SONICS_STATS_THREADS) k_evaluate_t(const EvalArgs a, int n_slots_cap,
+                                                                                  int smem_slots)
 {
     extern __shared__ __align__(16) unsigned char sm_raw[];
-    const int slot_ix = blockIdx.x;
+    typedef typename std::conditional<BIG, uint32_t, uint16_t>::type HT;
+    const int slot_ix = a.slot_base + blockIdx.x;
     const int g = a.active ? a.active[slot_ix] : slot_ix;
     const GtHeader h = a.t.hdr[g];
     const int A = h.n_alleles;
-    const int n = a.n_run, n_pad = a.n_pad;
+    const int n = a.n_run, n_pad = BIG ? a.n_run : a.n_pad;
     const int n_slots = a.random_start ? A * A : A;
     const int64_t base = (int64_t)g * a.out_stride;
 
-    StatsSmem m;
+    StatsArrays<HT> m;
     {
         unsigned char *p = sm_raw;
-        m.key = (unsigned long long *)p;
-        p += (size_t)n_pad * 8;
-        m.idx = (uint32_t *)p;
-        p += (size_t)(n_pad + 2) * 4;
-        m.S = (uint32_t *)p;
-        p += (size_t)(n_pad + 2) * 4;
-        m.slot = (uint16_t *)p;
-        p += (size_t)n_pad * 2;
-        m.thead = (uint16_t *)p;
-        p += (size_t)n_pad * 2;
-        m.tend = (uint16_t *)p;
-        p += (size_t)n_pad * 2;
-        p = (unsigned char *)(((uintptr_t)p + 7) & ~(uintptr_t)7);
-        m.maxk = (unsigned long long *)p;
-        p += (size_t)n_slots_cap * 8;
-        m.cnt = (int *)p;
-        p += (size_t)n_slots_cap * 4;
-        m.cnt_valid = (int *)p;
-        p += (size_t)n_slots_cap * 4;
-        p = (unsigned char *)(((uintptr_t)p + 7) & ~(uintptr_t)7);
+        if (BIG) {
+            const size_t o = (size_t)blockIdx.x * ((size_t)n + 1);
+            m.key = a.g_key + o;
+            m.idx = a.g_idx + o;
+            m.S = a.g_S + o;
+            m.slot = a.g_slot + o;
+            m.thead = (HT *)(a.g_thead + o);
+            m.tend = (HT *)(a.g_tend + o);
+        } else {
+            m.key = (unsigned long long *)p;
+            p += (size_t)n_pad * 8;
+            m.idx = (uint32_t *)p;
+            p += (size_t)(n_pad + 2) * 4;
+            m.S = (uint32_t *)p;
+            p += (size_t)(n_pad + 2) * 4;
+            m.slot = (uint16_t *)p;
+            p += (size_t)n_pad * 2;
+            m.thead = (HT *)p;
+            p += (size_t)n_pad * 2;
+            m.tend = (HT *)p;
+            p += (size_t)n_pad * 2;
+            p = (unsigned char *)(((uintptr_t)p + 7) & ~(uintptr_t)7);
+        }
+        if (!BIG || smem_slots) {
+            m.maxk = (unsigned long long *)p;
+            p += (size_t)n_slots_cap * 8;
+            m.cnt = (int *)p;
+            p += (size_t)n_slots_cap * 4;
+            m.cnt_valid = (int *)p;
+            p += (size_t)n_slots_cap * 4;
+            p = (unsigned char *)(((uintptr_t)p + 7) & ~(uintptr_t)7);
+        } else {
+            const size_t o = (size_t)blockIdx.x * n_slots_cap;
+            m.maxk = a.g_maxk + o;
+            m.cnt = a.g_cnt + o;
+            m.cnt_valid = a.g_cnt_valid + o;
+        }
         m.red = (double *)p;
         p += 32 * 8;
         m.wsum = (uint32_t *)p;
@@ -273,8 +378,10 @@ __global__ void __launch_bounds__(SONICS_STATS_THREADS) k_evaluate(const EvalArg
         if (i < n) {
             const double x = a.lnL[base + i];
             const unsigned long long k = f64_key(x);
-            m.key[i] = k;
-            m.idx[i] = (uint32_t)i;
+            if (!BIG) {
+                m.key[i] = k;
+                m.idx[i] = (uint32_t)i;
+            }
             const int s = slot_of(a.group[base + i], A, h.first_idx, a.random_start);
             atomicAdd(&m.cnt[s], 1);
             if (x > SONICS_SENTINEL)
@@ -287,26 +394,32 @@ __global__ void __launch_bounds__(SONICS_STATS_THREADS) k_evaluate(const EvalArg
     }
     __syncthreads();
 
-    // ---- 2. one global sort by lnL ----
-    bitonic_sort(m.key, m.idx, n_pad);
+    // ---- 2. one global sort by lnL (BIG: done by CUB before the launch; stable, so ties keep ascending indices
+    // exactly as the payload tie-break of the bitonic network orders them) ----
+    if (!BIG)
+        bitonic_sort(m.key, m.idx, n_pad);
 
     // ---- 3. slot of every sorted element, tie blocks ----
     for (int i = threadIdx.x; i < n; i += blockDim.x)
         m.slot[i] = (uint16_t)slot_of(a.group[base + m.idx[i]], A, h.first_idx, a.random_start);
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        // runs of equal keys are short except for the sentinel block at the bottom
-        if (i == 0 || m.key[i] != m.key[i - 1]) {
-            int e = i + 1;
-            while (e < n && m.key[e] == m.key[i])
-                ++e;
-            for (int j = i; j < e; ++j) {
-                m.thead[j] = (uint16_t)i;
-                m.tend[j] = (uint16_t)e; // n <= 8192 < 65536
+    if (BIG) {
+        tie_blocks_global(m.key, n, (uint32_t *)m.thead, (uint32_t *)m.tend, m.wsum);
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            // runs of equal keys are short except for the sentinel block at the bottom
+            if (i == 0 || m.key[i] != m.key[i - 1]) {
+                int e = i + 1;
+                while (e < n && m.key[e] == m.key[i])
+                    ++e;
+                for (int j = i; j < e; ++j) {
+                    m.thead[j] = (HT)i;
+                    m.tend[j] = (HT)e; // n <= 8192 < 65536
+                }
             }
         }
+        __syncthreads();
     }
-    __syncthreads();
 
     // ---- 4. groups present, min_sim, top two by max lnL (thread 0; a few dozen slots) ----
     if (threadIdx.x == 0) {
@@ -333,7 +446,7 @@ __global__ void __launch_bounds__(SONICS_STATS_THREADS) k_evaluate(const EvalArg
     v.n_groups = G;
     v.min_sim = min_sim;
 
-    if (a.monte_carlo) {
+    if (!BIG && a.monte_carlo) {
         // ---- MC mode (:115-131): best row = global max lnL; q75 of ident, r^2, lnL within its group ----
         const int gbest = m.slot[n - 1];
         // the reported row: lowest simulation index among the rows tied at the maximum

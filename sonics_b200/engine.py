@@ -309,7 +309,9 @@ class Engine:
         if active is not None:
             act_ptr, n_act = active.data_ptr(), int(active.numel())
         max_a = int(np.max(np.diff(table.allele_off)))
-        sbytes = int(self.lib.sonics_stats_scratch_bytes(int(n_run), max_a, int(params.random_start)))
+        sbytes = min(int(self.lib.sonics_stats_scratch_bytes_batch(n_act, int(n_run), max_a, int(params.random_start))),
+                     max(self.SCRATCH_CAP * 4, int(self.lib.sonics_stats_scratch_bytes(int(n_run), max_a,
+                                                                                      int(params.random_start)))))
         sptr, snum = None, 0
         if sbytes:
             sc = self._scratch_bytes(sbytes)
@@ -342,8 +344,8 @@ class Engine:
         n_gt = len(allele_off) - 1
         nc = None if noise_coef is None else np.ascontiguousarray(noise_coef, dtype=np.float32)
         ui = None if uid is None else np.ascontiguousarray(uid, dtype=np.uint32)
-        nbytes = self.lib.sonics_genotype_work_bytes_mode(n_gt, int(allele_off[-1]), int(max_reps),
-                                                          int(params.monte_carlo))
+        nbytes = self.lib.sonics_genotype_work_bytes_for(ctypes.byref(params), n_gt, allele_off.ctypes.data,
+                                                         int(max_reps))
         work = self._workspace(nbytes)
         out = np.zeros(n_gt, dtype=VERDICT_DTYPE)
         check(self.lib.sonics_genotype_batch(

@@ -330,3 +330,127 @@ def test_pass_with_min_sim_below_25_is_no_success():
     params = eng.make_params()
     v = e.verdicts_to_host(e.evaluate(params, table, out, 100, final_round=False))[0]
     assert v["filter"] == 0
+
+
+def _check_against_oracle_statistics(v, lnL, labels, min_sim_opt=25):
+    ev = stats.evaluate(lnL, labels, min_sim_opt)
+    assert v["min_sim"] == ev["min_sim"]
+    assert v["n_groups"] == len(ev["groups"])
+    if ev["evaluated"]:
+        assert "%d/%d" % (v["allele_lo"], v["allele_hi"]) == ev["best"]
+        assert v["best_lnL_ratio"] == ev["best_ratio"]
+        assert v["percentile_lnL_ratio"] == ev["pct_ratio"]
+        hp = min(ev["high_pval"], 1) if v["p_clamped"] else ev["high_pval"]
+        assert abs(v["high_pval"] - hp) <= 1e-10 * abs(hp) + 1e-300, (v["high_pval"], hp)
+    return ev
+
+
+def _labels(table, g, grp):
+    return np.array([table.group_label(g, int(x)) for x in grp])
+
+
+@pytest.mark.parametrize("n_run", [8192, 8193, 10000, 20000])
+def test_statistics_over_global_memory_match_the_oracle(n_run):
+    """-r above 8192: the statistics run over global-memory arrays sorted by CUB, many genotypes per launch
+    (n_run = 8192 is the last on-chip size: the two forms must agree with the oracle on both sides of the switch).
+    Checked per genotype against the numpy restatement of sonics.pyx:136-181 on the same lnL arrays, with a
+    scratch that holds all genotypes, with one that holds a single genotype (chunked launches), and through an
+    active list."""
+    e = engine()
+    t = e.torch
+    params = eng.make_params()
+    gts = [CFG1, CFG2, "14|700;15|2100;16|1900;17|2500;18|900;19|300", "9|100;10|100", "5|30;9|113;10|89;20|30"]
+    arrays = [orc.parse_reads(g) for g in gts]
+    table = e.build_table_from_arrays(params, arrays, [orc.auto_noise_coef(a) for a in arrays], uid=[5, 6, 7, 8, 9])
+    out = e.simulate(params, table, 20000, seed=21)
+    full = e.verdicts_to_host(e.evaluate(params, table, out, n_run, final_round=True)).copy()
+    for g in range(len(gts)):
+        lnL = out["lnL"][g, :n_run].cpu().numpy()
+        grp = out["group"][g, :n_run].cpu().numpy().view(np.uint16)
+        _check_against_oracle_statistics(full[g], lnL, _labels(table, g, grp))
+        assert full[g]["run_reps"] == n_run
+    if n_run > 8192:
+        keep, cap = e._scratch_buf, e.SCRATCH_CAP
+        try:
+            one = int(e.lib.sonics_stats_scratch_bytes(n_run, 8, 0))
+            assert one < int(e.lib.sonics_stats_scratch_bytes_batch(len(gts), n_run, 8, 0))
+            e._scratch_buf = t.empty(one, dtype=t.uint8, device=e.device)
+            e.SCRATCH_CAP = one // 4
+            chunked = e.verdicts_to_host(e.evaluate(params, table, out, n_run, final_round=True)).copy()
+        finally:
+            e._scratch_buf, e.SCRATCH_CAP = keep, cap
+        assert chunked.tobytes() == full.tobytes()
+    act = t.tensor([3, 1], dtype=t.int32, device=e.device)
+    part = e.verdicts_to_host(e.evaluate(params, table, out, n_run, final_round=True, active=act))
+    assert part[3].tobytes() == full[3].tobytes() and part[1].tobytes() == full[1].tobytes()
+    assert part[0]["run_reps"] == 0
+
+
+@pytest.mark.parametrize("max_reps", [10000, 50000])
+def test_controller_rounds_across_the_on_chip_limit(max_reps):
+    """Default mode with -r 10000 / 50000: rounds at 100 / 500 / 1000 / 5000 / 10000 (/ 50000) cumulative
+    simulations (sonics.pyx:79-82,193-199), the statistics switching from shared to global memory on the way.  The
+    device loop must print the row the oracle's monte_carlo() restatement prints when it is fed the very same
+    simulation records."""
+    e = engine()
+    params = eng.make_params()
+    gts = ["14|700;15|2100;16|1900;17|2500;18|900;19|300",   # MWU_test at every round: runs to max_reps
+           "5|30;9|113;10|89;20|30",                         # far allele without noise: no_success at max_reps
+           "9|60;10|40;11|30;12|8", CFG1, CFG2,
+           "12|40;13|60;14|55;15|35"]
+    arrays = [orc.parse_reads(g) for g in gts]
+    noise = [orc.auto_noise_coef(a) for a in arrays]
+    off, al, rd = eng.to_csr(arrays)
+    uid = np.arange(len(gts)) + 40
+    v = e.genotype_batch(params, off, al, rd, noise, max_reps, seed=31, uid=uid)
+    assert v[0]["run_reps"] == max_reps and v[1]["run_reps"] == max_reps and v[1]["filter"] == 16
+    assert stats.round_schedule(max_reps)[-3:] == ([1000, 5000, 10000] if max_reps == 10000 else [5000, 10000, 50000])
+    table = e.build_table(params, off, al, rd, noise, uid=uid)
+    out = e.simulate(params, table, max_reps, seed=31, readout=True)
+    e.sync()
+    for g in range(len(gts)):
+        lnL = out["lnL"][g].cpu().numpy()
+        ident = out["identity"][g].cpu().numpy()
+        r2 = out["rsq"][g].cpu().numpy().astype(np.float64)
+        lab = _labels(table, g, out["group"][g].cpu().numpy().view(np.uint16))
+        pos = [0]
+
+        def draw(n, lnL=lnL, ident=ident, r2=r2, lab=lab, pos=pos):
+            recs = [dict(identity=float(ident[i]), r_squared=float(r2[i]), lnL=float(lnL[i]), label=str(lab[i]))
+                    for i in range(pos[0], pos[0] + n)]
+            pos[0] += n
+            return recs
+        row, info = stats.monte_carlo(max_reps, draw)
+        got = drop_in.format_row(v[g], {"monte_carlo": False, "add_ratios": ""}).split("\t")
+        exp = row.split("\t")
+        assert got[:5] == exp[:5] and got[6:] == exp[6:], (g, got, exp)
+        if got[5] != exp[5]:
+            assert abs(float(got[5]) - float(exp[5])) <= 1e-10 * abs(float(exp[5])), (g, got[5], exp[5])
+
+
+def test_random_start_with_more_groups_than_shared_memory_holds():
+    """--random squares the number of genotype groups (sonics.pyx:320-321): 51 input alleles -> 1326 groups in
+    2601 slots, more than the on-chip statistics hold, and cfg3 (40 alleles -> 820 groups) at a simulation count
+    that gives every group its 25 valid rows.  Statistics over global memory against the oracle's on the same
+    arrays."""
+    e = engine()
+    params = eng.make_params(random=True, n_cycles=8, capture_cycle=5)
+    wide = ";".join("%d|%d" % (a, 30 + 5 * ((a * 7) % 11)) for a in range(10, 61))
+    arrays = [orc.parse_reads(wide), orc.parse_reads(CFG3)]
+    # noise molecules on every input allele (sonics.pyx:334-337): without them a pool grown from two start alleles
+    # misses most of the 40-51 input alleles and every simulation ends as the -999999 sentinel
+    table = e.build_table_from_arrays(params, arrays, [0.003, 0.003])
+    n = 120000
+    out = e.simulate(params, table, n, seed=41)
+    v = e.verdicts_to_host(e.evaluate(params, table, out, n, final_round=True))
+    for g, n_al in ((0, 51), (1, 40)):
+        lnL = out["lnL"][g].cpu().numpy()
+        grp = out["group"][g].cpu().numpy().view(np.uint16)
+        assert len(np.unique(grp)) == n_al * (n_al + 1) // 2
+        ev = _check_against_oracle_statistics(v[g], lnL, _labels(table, g, grp))
+        assert v[g]["n_groups"] == n_al * (n_al + 1) // 2
+        print("genotype %d: %d groups, min_sim %d, evaluated %s" % (g, v[g]["n_groups"], v[g]["min_sim"], ev["evaluated"]))
+    # the whole loop accepts such a genotype (it used to be rejected: 'use fewer alleles with --random')
+    off, al, rd = eng.to_csr(arrays[:1])
+    w = e.genotype_batch(params, off, al, rd, [0.003], 1000, seed=42)
+    assert w[0]["run_reps"] == 1000 and w[0]["n_groups"] > 300
