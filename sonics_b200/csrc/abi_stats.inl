@@ -82,17 +82,21 @@ static int global_layout(int64_t c, int64_t n, int n_slots, GlobalLayout &L)
     size_t tmp = 0;
     cub::DoubleBuffer<unsigned long long> dk(nullptr, nullptr);
     cub::DoubleBuffer<uint32_t> dv(nullptr, nullptr);
-    cudaError_t e;
-    if (c == 1) {
-        e = cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)n, 0, 64);
-    } else {
+    // the last chunk of a launch sequence may hold a single genotype, which is sorted by the plain radix sort:
+    // the temporary storage covers both forms
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)n, 0, 64);
+    if (e != cudaSuccess)
+        return -1;
+    if (c > 1) {
+        size_t tmp_seg = 0;
         cub::CountingInputIterator<int> iota(0);
         SegBeginIt b(iota, SegBegin{(int)(n + 1)});
         SegEndIt en(iota, SegEnd{(int)(n + 1), (int)n});
-        e = cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)N, (int)c, b, en, 0, 64);
+        e = cub::DeviceSegmentedRadixSort::SortPairs(nullptr, tmp_seg, dk, dv, (int)N, (int)c, b, en, 0, 64);
+        if (e != cudaSuccess)
+            return -1;
+        tmp = std::max(tmp, tmp_seg);
     }
-    if (e != cudaSuccess)
-        return -1;
     L.tmp_bytes = big_align(tmp) + 256;
     L.total = o + L.tmp_bytes;
     return 0;

@@ -34,6 +34,20 @@ namespace sonics {
 // from hanging the warp.
 #define SONICS_LS_MAX_TRIALS 4096
 
+// Diagnostics build only (-DSONICS_LS_STATS, tools/ls_stats.py): warp-level counters of the lockstep schedule.
+#ifdef SONICS_LS_STATS
+__device__ unsigned long long g_ls_stats[128];
+#define LS_STAT(i, v)                                                                                                  \
+    do {                                                                                                               \
+        if ((threadIdx.x & 31) == 0)                                                                                   \
+            atomicAdd(&g_ls_stats[i], (unsigned long long)(v));                                                        \
+    } while (0)
+#else
+#define LS_STAT(i, v)                                                                                                  \
+    do {                                                                                                               \
+    } while (0)
+#endif
+
 struct SortCfg {
     int grp_bits, eff_bits, dn_bits, up_bits;
 };
@@ -95,15 +109,41 @@ __device__ __forceinline__ int binomial_ls(PairRng &rng, int n, float p, const f
     bool pend = need && !inv;
     int guard = 0;
     DrawState ds;
+#ifdef SONICS_LS_STATS
+    {
+        const unsigned mp = __ballot_sync(SONICS_FULL, pend), mi = __ballot_sync(SONICS_FULL, inv);
+        LS_STAT(1, 1);
+        LS_STAT(2, mp != 0);
+        LS_STAT(3, mi != 0);
+        LS_STAT(4, mp != 0 && mi != 0);
+        LS_STAT(5, __popc(mp));
+        LS_STAT(6, __popc(mi));
+        // lanes by log2(n p q) of their BTRS draw
+        const float npq = (float)n * pp * (1.0f - pp);
+        const int bk = pend ? min(15, max(0, (int)floorf(log2f(npq)))) : -1;
+        for (int k = 3; k < 16; ++k)
+            LS_STAT(32 + k, __popc(__ballot_sync(SONICS_FULL, bk == k)));
+    }
+    int rounds = 0;
+#endif
     if (__any_sync(SONICS_FULL, pend)) {
         if (pend)
             btrs_setup(ds, n, pp);
         // The exact test of an undecided candidate runs inside the round (deferring it to a common point was
         // measured: fewer executions, but the lanes it sends back retry alone -- 7.85e7 vs 8.46e7 reactions/s).
         do {
+#ifdef SONICS_LS_STATS
+            ++rounds;
+            LS_STAT(7, 1);
+            LS_STAT(8, __popc(__ballot_sync(SONICS_FULL, pend)));
+            bool und = false;
+#endif
             if (pend) {
                 const uint2 w = rng.pair();
                 int r = btrs_trial(ds, w.x, w.y);
+#ifdef SONICS_LS_STATS
+                und = r == 2;
+#endif
                 if (r == 2)
                     r = btrs_full(ds) ? 1 : 0;
                 if (r == 1) {
@@ -112,7 +152,17 @@ __device__ __forceinline__ int binomial_ls(PairRng &rng, int n, float p, const f
                     pend = false;
                 }
             }
+#ifdef SONICS_LS_STATS
+            {
+                const unsigned mu = __ballot_sync(SONICS_FULL, und);
+                LS_STAT(9, mu != 0);
+                LS_STAT(10, __popc(mu));
+            }
+#endif
         } while (__any_sync(SONICS_FULL, pend) && ++guard < SONICS_LS_MAX_TRIALS);
+#ifdef SONICS_LS_STATS
+        LS_STAT(16 + min(rounds, 15), 1);
+#endif
     }
     if (__any_sync(SONICS_FULL, inv)) {
         if (inv) {
@@ -122,6 +172,13 @@ __device__ __forceinline__ int binomial_ls(PairRng &rng, int n, float p, const f
             inv_run(ds, rcp_tab);
             x = flip ? n - ds.ix : ds.ix;
         }
+#ifdef SONICS_LS_STATS
+        {
+            const int steps = inv ? ds.ix : 0;
+            LS_STAT(11, __reduce_max_sync(SONICS_FULL, steps));
+            LS_STAT(12, __reduce_add_sync(SONICS_FULL, steps));
+        }
+#endif
     }
     return x;
 }
@@ -181,6 +238,7 @@ __global__ void __launch_bounds__(128, SONICS_LS_MIN_BLOCKS) k_pcr_ls(const SimA
             break;
         const int idx = (int)batch * 32 + lane;
         bool valid = idx < a.n_units;
+        LS_STAT(0, 1);
 
         // ---- per-lane set-up: priors, start alleles, start pool (sonics.pyx:302-337) ----
         int u = 0, g = 0, jrel = 0, W = 0, lo = 0, floor_bin = 0;
@@ -302,6 +360,8 @@ __global__ void __launch_bounds__(128, SONICS_LS_MIN_BLOCKS) k_pcr_ls(const SimA
             }
             for (int b = wlo; b <= wend; ++b) {
                 const bool in = b >= sb && b <= bend;
+                LS_STAT(13, 1);
+                LS_STAT(14, __popc(__ballot_sync(SONICS_FULL, in)));
                 int cur = 0, n0 = 0;
                 bool stutter = false;
                 float p_slip = 0.0f, p_upn = 0.0f;
@@ -330,6 +390,8 @@ __global__ void __launch_bounds__(128, SONICS_LS_MIN_BLOCKS) k_pcr_ls(const SimA
                     const float dp = stage == 0 ? eff : (stage == 1 ? p_slip : p_upn);
                     if (!__any_sync(SONICS_FULL, dn > 0))
                         break; // nothing amplified / slipped in any lane: the later stages draw from 0
+                    LS_STAT(48 + stage, 1);
+                    LS_STAT(52 + stage, __popc(__ballot_sync(SONICS_FULL, dn > 0)));
                     const int x = binomial_ls(rng, dn, dp, rcp_tab);
                     if (stage == 0)
                         x0 = x;

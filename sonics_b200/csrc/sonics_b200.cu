@@ -542,6 +542,19 @@ size_t sonics_scratch_bytes(int64_t n_units, int max_window)
     return sonics_scratch_bytes_kernel(n_units, max_window, SONICS_KERNEL_LOCKSTEP);
 }
 
+#ifdef SONICS_LS_STATS
+// diagnostics build only: read and clear the lockstep schedule counters (tools/ls_stats.py)
+int sonics_debug_ls_stats(uint64_t *host_out128)
+{
+    unsigned long long z[128] = {0};
+    if (cudaMemcpyFromSymbol(host_out128, g_ls_stats, sizeof(z)) != cudaSuccess)
+        return SONICS_ERR_CUDA;
+    if (cudaMemcpyToSymbol(g_ls_stats, z, sizeof(z)) != cudaSuccess)
+        return SONICS_ERR_CUDA;
+    return SONICS_OK;
+}
+#endif
+
 int sonics_set_kernel(sonics_ctx *ctx, int kernel)
 {
     if (!ctx || kernel < SONICS_KERNEL_AUTO || kernel > SONICS_KERNEL_LOCKSTEP)

@@ -12,7 +12,7 @@ from oracle import stats
 from sonics_b200 import engine as eng
 from sonics_b200 import sonics as drop_in
 from tests.gpu_util import engine
-from tests.util import CFG1, CFG2, cfg_from_case, load
+from tests.util import CFG1, CFG2, CFG3, cfg_from_case, load
 
 pytestmark = pytest.mark.gpu
 
@@ -359,9 +359,11 @@ def test_statistics_over_global_memory_match_the_oracle(n_run):
     e = engine()
     t = e.torch
     params = eng.make_params()
-    gts = [CFG1, CFG2, "14|700;15|2100;16|1900;17|2500;18|900;19|300", "9|100;10|100", "5|30;9|113;10|89;20|30"]
+    five = [CFG1, CFG2, "14|700;15|2100;16|1900;17|2500;18|900;19|300", "9|100;10|100", "5|30;9|113;10|89;20|30"]
+    gts = five + five + five[:1]  # 11 genotypes (distinct RNG uids): chunks of several genotypes and a tail of one
     arrays = [orc.parse_reads(g) for g in gts]
-    table = e.build_table_from_arrays(params, arrays, [orc.auto_noise_coef(a) for a in arrays], uid=[5, 6, 7, 8, 9])
+    table = e.build_table_from_arrays(params, arrays, [orc.auto_noise_coef(a) for a in arrays],
+                                      uid=list(range(5, 5 + len(gts))))
     out = e.simulate(params, table, 20000, seed=21)
     full = e.verdicts_to_host(e.evaluate(params, table, out, n_run, final_round=True)).copy()
     for g in range(len(gts)):
@@ -374,12 +376,13 @@ def test_statistics_over_global_memory_match_the_oracle(n_run):
         try:
             one = int(e.lib.sonics_stats_scratch_bytes(n_run, 8, 0))
             assert one < int(e.lib.sonics_stats_scratch_bytes_batch(len(gts), n_run, 8, 0))
-            e._scratch_buf = t.empty(one, dtype=t.uint8, device=e.device)
-            e.SCRATCH_CAP = one // 4
-            chunked = e.verdicts_to_host(e.evaluate(params, table, out, n_run, final_round=True)).copy()
+            for size in (one, (one * 5) // 2):
+                e._scratch_buf = t.empty(size, dtype=t.uint8, device=e.device)
+                e.SCRATCH_CAP = size // 4
+                chunked = e.verdicts_to_host(e.evaluate(params, table, out, n_run, final_round=True)).copy()
+                assert chunked.tobytes() == full.tobytes()
         finally:
             e._scratch_buf, e.SCRATCH_CAP = keep, cap
-        assert chunked.tobytes() == full.tobytes()
     act = t.tensor([3, 1], dtype=t.int32, device=e.device)
     part = e.verdicts_to_host(e.evaluate(params, table, out, n_run, final_round=True, active=act))
     assert part[3].tobytes() == full[3].tobytes() and part[1].tobytes() == full[1].tobytes()
@@ -394,16 +397,19 @@ def test_controller_rounds_across_the_on_chip_limit(max_reps):
     simulation records."""
     e = engine()
     params = eng.make_params()
-    gts = ["14|700;15|2100;16|1900;17|2500;18|900;19|300",   # MWU_test at every round: runs to max_reps
+    gts = ["9|2;10|3;11|2",                                  # 7 reads: lnL ratios below 2.3, evaluated every round
            "5|30;9|113;10|89;20|30",                         # far allele without noise: no_success at max_reps
            "9|60;10|40;11|30;12|8", CFG1, CFG2,
-           "12|40;13|60;14|55;15|35"]
+           "12|40;13|60;14|55;15|35", "14|700;15|2100;16|1900;17|2500;18|900;19|300"]
     arrays = [orc.parse_reads(g) for g in gts]
     noise = [orc.auto_noise_coef(a) for a in arrays]
     off, al, rd = eng.to_csr(arrays)
     uid = np.arange(len(gts)) + 40
     v = e.genotype_batch(params, off, al, rd, noise, max_reps, seed=31, uid=uid)
-    assert v[0]["run_reps"] == max_reps and v[1]["run_reps"] == max_reps and v[1]["filter"] == 16
+    print("run_reps", [int(x) for x in v["run_reps"]], "filter", [int(x) for x in v["filter"]])
+    assert v[1]["run_reps"] == max_reps and v[1]["filter"] == 16
+    # at least one genotype is still being evaluated (not no_success) when the statistics leave shared memory
+    assert any(v[g]["run_reps"] > 8192 and v[g]["filter"] != 16 for g in range(len(gts)))
     assert stats.round_schedule(max_reps)[-3:] == ([1000, 5000, 10000] if max_reps == 10000 else [5000, 10000, 50000])
     table = e.build_table(params, off, al, rd, noise, uid=uid)
     out = e.simulate(params, table, max_reps, seed=31, readout=True)
