@@ -174,6 +174,16 @@ int sonics_set_kernel(sonics_ctx *ctx, int kernel);
  * sort only decides which lane runs which simulation: results never depend on it (tuning knob; env
  * SONICS_SORT_BITS=e,d,u sets the initial value). */
 int sonics_set_sort_bits(sonics_ctx *ctx, int eff_bits, int down_bits, int up_bits);
+/* Lockstep form, launches over many genotypes: which simulations share a warp.
+ *   SONICS_SORT_PAIR_MAJOR (default)  noise flag | the two start alleles as absolute repeat counts | priors: a reaction
+ *                                     depends on its start alleles and priors, the genotype's reads only enter the
+ *                                     lnL, so equal start pairs of ALL genotypes of the launch are pooled (a
+ *                                     genotyping round runs 100-400 simulations per genotype, 12-50 per start pair:
+ *                                     less than a warp);
+ *   SONICS_SORT_SLOT_MAJOR            genotype | start-allele group | priors (what a single-genotype launch uses).
+ * Results never depend on it (env SONICS_SORT_MODE=pair|slot sets the initial value). */
+enum { SONICS_SORT_PAIR_MAJOR = 0, SONICS_SORT_SLOT_MAJOR = 1 };
+int sonics_set_sort_mode(sonics_ctx *ctx, int mode);
 /* Scratch for sonics_simulate / sonics_replay_best.  Lockstep form: sort keys and unit order, 24 bytes per work
  * unit + CUB temporary storage.  Persistent form: the final PCR pools of the work units of one chunk (K1a -> K1b
  * hand-off, 128 * max_window bytes per 32 units).  sonics_scratch_bytes(n_units, max_window) is the size that runs

@@ -37,10 +37,12 @@ namespace sonics {
 // Diagnostics build only (-DSONICS_LS_STATS, tools/ls_stats.py): warp-level counters of the lockstep schedule.
 #ifdef SONICS_LS_STATS
 __device__ unsigned long long g_ls_stats[128];
+__shared__ unsigned int s_ls_stats[4][128]; // per warp, written by lane 0, flushed when the warp leaves the kernel
 #define LS_STAT(i, v)                                                                                                  \
     do {                                                                                                               \
+        const unsigned int ls_v_ = (unsigned int)(v); /* warp-wide votes in v run with all lanes */                    \
         if ((threadIdx.x & 31) == 0)                                                                                   \
-            atomicAdd(&g_ls_stats[i], (unsigned long long)(v));                                                        \
+            s_ls_stats[threadIdx.x >> 5][i] += ls_v_;                                                                  \
     } while (0)
 #else
 #define LS_STAT(i, v)                                                                                                  \
@@ -48,9 +50,24 @@ __device__ unsigned long long g_ls_stats[128];
     } while (0)
 #endif
 
+// Sort key of a work unit.
+// pair_major = 0 (one genotype per launch): slot | start-allele group | eff | down | up (quantised priors).
+// pair_major = 1 (many genotypes per launch): what a reaction does depends on its start alleles, the noise molecules
+// and its priors -- the genotype's reads only enter the lnL -- so the 100-400 simulations a genotyping round runs per
+// genotype (12-50 per start-allele group, less than a warp) are pooled with the like simulations of every other
+// genotype of the launch:
+//     noise flag | lower, higher start allele (absolute repeat counts) | reach of the noise below / above them | priors
+// (noise molecules sit on every input allele, sonics.pyx:334-337: with them the live bins of a reaction are the
+// genotype's whole input range; 85 % of the genotypes of a lobSTR-style VCF get them from the automatic rule,
+// sonics:407-416).  The three priors are interleaved bit by bit (Morton order), so any run of 32 neighbours of the
+// sorted list is as compact in (eff, down, up) as the population of its cell allows, whatever that population is.
 struct SortCfg {
-    int grp_bits, eff_bits, dn_bits, up_bits;
+    int grp_bits, eff_bits, dn_bits, up_bits, pair_major;
 };
+#define SONICS_LS_ALLELE_BITS 9 // SONICS_MAX_ALLELE = 500
+#define SONICS_LS_REACH_BITS 5
+#define SONICS_LS_MORTON_BITS 5 // per prior
+#define SONICS_LS_PAIR_KEY_BITS (1 + 2 * SONICS_LS_ALLELE_BITS + 2 * SONICS_LS_REACH_BITS + 3 * SONICS_LS_MORTON_BITS)
 
 template <typename KeyT>
 __global__ void k_sort_keys(const SimArgs a, const SortCfg c, KeyT *keys, uint32_t *vals)
@@ -79,15 +96,35 @@ __global__ void k_sort_keys(const SimArgs a, const SortCfg c, KeyT *keys, uint32
         const int q = (int)(t * (double)(1 << bits));
         return (uint32_t)max(0, min(q, (1 << bits) - 1));
     };
-    const uint32_t qe = quant(pr.eff, a.p.eff_lo, a.p.eff_rng, c.eff_bits);
-    const uint32_t qd = quant(pr.down, a.p.down_lo, a.p.down_rng, c.dn_bits);
     const double up_rng = a.p.up_preference ? a.p.up_hi - a.p.up_lo : a.p.down_lo + a.p.down_rng - a.p.up_lo;
-    const uint32_t qu = quant(pr.up, a.p.up_lo, up_rng, c.up_bits);
-    KeyT k = (KeyT)slot;
-    k = (k << c.grp_bits) | (KeyT)(gid & ((1u << c.grp_bits) - 1u));
-    k = (k << c.eff_bits) | (KeyT)qe;
-    k = (k << c.dn_bits) | (KeyT)qd;
-    k = (k << c.up_bits) | (KeyT)qu;
+    KeyT k;
+    if (c.pair_major) {
+        const int v1 = a.t.allele[h.a_off + pr.i1], v2 = a.t.allele[h.a_off + pr.i2];
+        const int vlo = min(v1, v2), vhi = max(v1, v2);
+        const bool noisy = h.noise_add > 0;
+        const int reach_cap = (1 << SONICS_LS_REACH_BITS) - 1;
+        const int below = noisy ? min(vlo - (h.lo + h.in_lo_bin), reach_cap) : 0;
+        const int above = noisy ? min(a.t.allele[h.a_off + h.n_alleles - 1] - vhi, reach_cap) : 0;
+        k = (KeyT)(noisy ? 1 : 0);
+        k = (k << SONICS_LS_ALLELE_BITS) | (KeyT)vlo;
+        k = (k << SONICS_LS_ALLELE_BITS) | (KeyT)vhi;
+        k = (k << SONICS_LS_REACH_BITS) | (KeyT)below;
+        k = (k << SONICS_LS_REACH_BITS) | (KeyT)above;
+        const uint32_t qe = quant(pr.eff, a.p.eff_lo, a.p.eff_rng, SONICS_LS_MORTON_BITS);
+        const uint32_t qd = quant(pr.down, a.p.down_lo, a.p.down_rng, SONICS_LS_MORTON_BITS);
+        const uint32_t qu = quant(pr.up, a.p.up_lo, up_rng, SONICS_LS_MORTON_BITS);
+        for (int i = SONICS_LS_MORTON_BITS - 1; i >= 0; --i)
+            k = (k << 3) | (KeyT)((((qe >> i) & 1u) << 2) | (((qd >> i) & 1u) << 1) | ((qu >> i) & 1u));
+    } else {
+        const uint32_t qe = quant(pr.eff, a.p.eff_lo, a.p.eff_rng, c.eff_bits);
+        const uint32_t qd = quant(pr.down, a.p.down_lo, a.p.down_rng, c.dn_bits);
+        const uint32_t qu = quant(pr.up, a.p.up_lo, up_rng, c.up_bits);
+        k = (KeyT)slot;
+        k = (k << c.grp_bits) | (KeyT)(gid & ((1u << c.grp_bits) - 1u));
+        k = (k << c.eff_bits) | (KeyT)qe;
+        k = (k << c.dn_bits) | (KeyT)qd;
+        k = (k << c.up_bits) | (KeyT)qu;
+    }
     keys[u] = k;
     vals[u] = (uint32_t)u;
 }
@@ -223,6 +260,10 @@ __global__ void __launch_bounds__(128, SONICS_LS_MIN_BLOCKS) k_pcr_ls(const SimA
     float *rcp_tab = reinterpret_cast<float *>(smem_raw);
     for (int i = threadIdx.x; i < SONICS_RCP_TABLE; i += blockDim.x)
         rcp_tab[i] = i ? 1.0f / (float)i : 0.0f;
+#ifdef SONICS_LS_STATS
+    for (int i = lane; i < 128; i += 32)
+        s_ls_stats[warp][i] = 0;
+#endif
     __syncthreads();
     int *hist = reinterpret_cast<int *>(smem_raw + SONICS_RCP_TABLE * 4 + (size_t)warp * warp_smem_bytes(Wcap)) + lane;
     const int n_cycles = a.p.n_cycles, cap_cycle = a.p.capture_cycle;
@@ -310,10 +351,12 @@ __global__ void __launch_bounds__(128, SONICS_LS_MIN_BLOCKS) k_pcr_ls(const SimA
             if (cycle == cap_cycle) {
                 // capture step (:412-423): max count, first non-zero allele, non-zero count; then one Poisson
                 // draw per non-zero bin
-                const int wl = __reduce_min_sync(SONICS_FULL, live_lo);
-                const int wh = __reduce_max_sync(SONICS_FULL, live_hi);
+                // the warp walks ABSOLUTE repeat counts (lanes of different genotypes have different window origins)
+                const int wl = __reduce_min_sync(SONICS_FULL, lo + live_lo);
+                const int wh = __reduce_max_sync(SONICS_FULL, lo + live_hi);
                 int maxp = 0, nnz = 0, minidx = -1;
-                for (int c = wl; c <= wh; ++c) {
+                for (int cw = wl; cw <= wh; ++cw) {
+                    const int c = cw - lo;
                     if (c >= live_lo && c <= live_hi) {
                         const int v = hist[c * 32];
                         maxp = max(maxp, v);
@@ -330,7 +373,8 @@ __global__ void __launch_bounds__(128, SONICS_LS_MIN_BLOCKS) k_pcr_ls(const SimA
                     floor_cap = (float)(1.0 - ((double)__fmul_rn(cap_set, (float)nnz)) / 2.0);
                 }
                 int cap_n = 1;
-                for (int c = wl; c <= wh; ++c) {
+                for (int cw = wl; cw <= wh; ++cw) {
+                    const int c = cw - lo;
                     const int v = (nnz > 0 && c >= live_lo && c <= live_hi) ? hist[c * 32] : 0;
                     float lam = 0.0f;
                     if (v != 0) {
@@ -348,8 +392,8 @@ __global__ void __launch_bounds__(128, SONICS_LS_MIN_BLOCKS) k_pcr_ls(const SimA
             // ---- amplification sweep of this cycle (:424-479) ----
             const int sb = live_lo;
             const int bend = valid ? min(live_hi + 1, W - 1) : -1;
-            const int wlo = __reduce_min_sync(SONICS_FULL, sb);
-            const int wend = __reduce_max_sync(SONICS_FULL, bend);
+            const int wlo = __reduce_min_sync(SONICS_FULL, lo + sb);
+            const int wend = __reduce_max_sync(SONICS_FULL, lo + bend);
             int carry = 0;
             int prev = (valid && sb > 0) ? hist[(sb - 1) * 32] : 0; // finished value of bin b-1
             float E_up = 0.0f, E_dn = 0.0f;
@@ -358,7 +402,8 @@ __global__ void __launch_bounds__(128, SONICS_LS_MIN_BLOCKS) k_pcr_ls(const SimA
                 E_up = expm1f(__fmul_rn(al, l_up));
                 E_dn = expm1f(__fmul_rn(al, l_dn));
             }
-            for (int b = wlo; b <= wend; ++b) {
+            for (int bw = wlo; bw <= wend; ++bw) {
+                const int b = bw - lo;
                 const bool in = b >= sb && b <= bend;
                 LS_STAT(13, 1);
                 LS_STAT(14, __popc(__ballot_sync(SONICS_FULL, in)));
@@ -448,6 +493,13 @@ __global__ void __launch_bounds__(128, SONICS_LS_MIN_BLOCKS) k_pcr_ls(const SimA
             }
         }
         __syncwarp();
+#ifdef SONICS_LS_STATS
+        for (int i = lane; i < 128; i += 32) { // flushed per batch: the 32-bit counters cannot wrap
+            atomicAdd(&g_ls_stats[i], (unsigned long long)s_ls_stats[warp][i]);
+            s_ls_stats[warp][i] = 0;
+        }
+        __syncwarp();
+#endif
     }
 }
 

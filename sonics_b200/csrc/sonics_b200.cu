@@ -58,6 +58,7 @@ struct sonics_ctx {
     int32_t *readout_dump;   // sonics_debug_readout
     int kernel;              // SONICS_KERNEL_*: which form of K1 sonics_simulate launches
     int sort_bits[3];        // lockstep sort key: bits of efficiency / down / up (-1 = automatic)
+    int sort_mode;           // SONICS_SORT_*
     std::map<const void *, TableInfo> tables;
 };
 
@@ -114,6 +115,10 @@ int sonics_create(int device, sonics_ctx **out)
     }
     if (const char *e = getenv("SONICS_SORT_BITS"))
         sscanf(e, "%d,%d,%d", &c->sort_bits[0], &c->sort_bits[1], &c->sort_bits[2]);
+    c->sort_mode = SONICS_SORT_PAIR_MAJOR;
+    if (const char *e = getenv("SONICS_SORT_MODE"))
+        if (!strcmp(e, "slot"))
+            c->sort_mode = SONICS_SORT_SLOT_MAJOR;
     *out = c;
     return SONICS_OK;
 }
@@ -447,6 +452,8 @@ static int launch_simulate_lockstep(sonics_ctx *ctx, SimArgs &a, const TableInfo
     SortCfg sc;
     sc.grp_bits = bits_for(n_groups);
     const int slot_bits = bits_for(n_slots);
+    // many genotypes per launch: pool the simulations of equal start pairs across genotypes (see SortCfg)
+    sc.pair_major = (n_slots > 1 && a.sims_per_gt > 1 && ctx->sort_mode != SONICS_SORT_SLOT_MAJOR) ? 1 : 0;
     const double per_group = (double)a.sims_per_gt / (double)(a.p.random_start ? (int64_t)A * (A + 1) / 2 : A);
     int pbits = 0;
     while (pbits < 15 && per_group / (double)(1 << (pbits + 1)) >= 32.0)
@@ -460,7 +467,9 @@ static int launch_simulate_lockstep(sonics_ctx *ctx, SimArgs &a, const TableInfo
         sc.up_bits = std::min(std::max(ctx->sort_bits[2], 0), 15);
     }
     // one simulation per genotype (K4 replay): the list is already in genotype order
-    const int key_bits = a.sims_per_gt == 1 ? 0 : slot_bits + sc.grp_bits + sc.eff_bits + sc.dn_bits + sc.up_bits;
+    const int key_bits = a.sims_per_gt == 1 ? 0
+                         : sc.pair_major ? SONICS_LS_PAIR_KEY_BITS
+                                         : slot_bits + sc.grp_bits + sc.eff_bits + sc.dn_bits + sc.up_bits;
     if (key_bits > 64)
         return fail(SONICS_ERR_RANGE, "sort key of %d bits", key_bits);
 
@@ -560,6 +569,14 @@ int sonics_set_kernel(sonics_ctx *ctx, int kernel)
     if (!ctx || kernel < SONICS_KERNEL_AUTO || kernel > SONICS_KERNEL_LOCKSTEP)
         return fail(SONICS_ERR_ARG, "sonics_set_kernel: bad argument");
     ctx->kernel = kernel;
+    return SONICS_OK;
+}
+
+int sonics_set_sort_mode(sonics_ctx *ctx, int mode)
+{
+    if (!ctx || (mode != SONICS_SORT_PAIR_MAJOR && mode != SONICS_SORT_SLOT_MAJOR))
+        return fail(SONICS_ERR_ARG, "sonics_set_sort_mode: bad argument");
+    ctx->sort_mode = mode;
     return SONICS_OK;
 }
 

@@ -120,3 +120,38 @@ def test_sort_key_bits_do_not_change_results():
             _assert_same(ref, got)
     finally:
         check(e.lib.sonics_set_sort_bits(e.ctx, -1, -1, -1))
+
+
+def test_pair_major_sort_pools_start_pairs_across_genotypes():
+    """Launches over many genotypes sort by (noise flag, the two start alleles as absolute repeat counts, priors):
+    a warp then holds simulations of different genotypes -- different window origins, reads, allele lists, some
+    with noise molecules.  Same results as the genotype-major order and as the persistent form."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools"))
+    import synth_vcf
+    from sonics_b200 import driver
+    from sonics_b200._abi import check
+    loci = synth_vcf.make_genotypes(40, 4, seed=77, cov=(60, 900))
+    pre = {"one_allele_threshold": 45, "noise_threshold": 0.05}
+    work = [pl for k, pl in (driver.prefilter(t, pre, {"monte_carlo": False}) for t in synth_vcf.genotype_strings(loci))
+            if k == "sim"]
+    reads = [w[0] for w in work] + [orc.parse_reads("9|1;10|54;11|914;12|15"), orc.parse_reads("30|5;31|400;32|9")]
+    noise = [float(np.float32(w[1])) for w in work] + [0.0011, 0.004]
+    assert len(reads) > 100 and any(n > 0 for n in noise)
+    e = engine()
+    p = eng.make_params()
+    table = e.build_table_from_arrays(p, reads, noise)
+    res = {}
+    try:
+        for name, kernel, mode in (("persistent", "persistent", 0), ("pair", "lockstep", 0), ("slot", "lockstep", 1)):
+            e.set_kernel(kernel)
+            check(e.lib.sonics_set_sort_mode(e.ctx, mode))
+            out = e.simulate(p, table, 100, seed=21, readout=True, simpar=True)
+            e.sync()
+            res[name] = {k: v.cpu().numpy() for k, v in out.items()}
+    finally:
+        e.set_kernel("auto")
+        check(e.lib.sonics_set_sort_mode(e.ctx, 0))
+    _assert_same(res["persistent"], res["pair"])
+    _assert_same(res["persistent"], res["slot"])

@@ -52,7 +52,7 @@ def main():
                                ("cfg3", CFG3, dict(n_cycles=30, capture_cycle=16), max(n // 8, 1000))):
         kind, (reads, nc) = driver.prefilter(("sample", "Block", ".", spec), pre, {"monte_carlo": True})
         cases.append((name, [reads], [float(np.float32(nc))], kw, nn))
-    loci = synth_vcf.make_genotypes(250, 8, seed=20261019)
+    loci = synth_vcf.make_genotypes(int(os.environ.get("SONICS_AB_LOCI", "250")), 8, seed=20261019, cov=(50, 1000))
     work = [p for k, p in (driver.prefilter(t, pre, {"monte_carlo": False}) for t in synth_vcf.genotype_strings(loci))
             if k == "sim"]
     for reps in (100, 400):
@@ -70,6 +70,13 @@ def main():
                 if kernel == "lockstep":
                     b = (-1, -1, -1) if bits == "auto" else tuple(int(x) for x in bits.split(","))
                     check(e.lib.sonics_set_sort_bits(e.ctx, *b))
+                for mode in ((0, 1) if kernel == "lockstep" and table.n_gt > 1 else (0,)):
+                    check(e.lib.sonics_set_sort_mode(e.ctx, mode))
+                    ms, out = timed(e, params, table, nn)
+                    if mode == 1:
+                        print(json.dumps({"workload": name, "kernel": kernel, "sort_bits": bits, "sort_mode": "slot",
+                                          "reactions": total, "ms": ms, "reactions_per_s": total / ms * 1e3}), flush=True)
+                check(e.lib.sonics_set_sort_mode(e.ctx, 0))
                 ms, out = timed(e, params, table, nn)
                 h = out["lnL"].cpu().numpy().tobytes()
                 same = ref is None or h == ref

@@ -30,26 +30,45 @@ def run(name, n):
     from sonics_b200.sonics import get_alleles
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     import k1_ab
-    spec, kw = {"cfg1": (k1_ab.CFG1, {}), "cfg2": (k1_ab.CFG2, {}),
-                "cfg3": (k1_ab.CFG3, dict(n_cycles=30, capture_cycle=16))}[name]
     e = eng.Engine(0)
     e.set_kernel("lockstep")
-    params = eng.make_params(**kw)
-    reads = get_alleles(spec)[0]
-    nz = reads[reads > 0]
-    frac = nz.min() / reads.sum() * len(nz)
-    nc = float(nz.min() / reads.sum()) if frac / (frac + 1) < 0.05 else 0.0
-    table = e.build_table_from_arrays(params, [reads], [nc])
+    if name.startswith("vcf"):
+        # vcf:<loci>:<pair|slot>  -- a cfg4-style table, n simulations per genotype
+        import synth_vcf
+        from sonics_b200 import driver
+        _, n_loci, mode = name.split(":")
+        loci = synth_vcf.make_genotypes(int(n_loci), 8, seed=20261019, cov=(50, 1000))
+        pre = {"one_allele_threshold": 45, "noise_threshold": 0.05}
+        work = [p for k, p in (driver.prefilter(t, pre, {"monte_carlo": False})
+                               for t in synth_vcf.genotype_strings(loci)) if k == "sim"]
+        params = eng.make_params()
+        table = e.build_table_from_arrays(params, [w[0] for w in work], [float(np.float32(w[1])) for w in work])
+        e.lib.sonics_set_sort_mode(e.ctx, 1 if mode == "slot" else 0)
+    else:
+        spec, kw = {"cfg1": (k1_ab.CFG1, {}), "cfg2": (k1_ab.CFG2, {}),
+                    "cfg3": (k1_ab.CFG3, dict(n_cycles=30, capture_cycle=16))}[name]
+        params = eng.make_params(**kw)
+        reads = get_alleles(spec)[0]
+        nz = reads[reads > 0]
+        frac = nz.min() / reads.sum() * len(nz)
+        nc = float(nz.min() / reads.sum()) if frac / (frac + 1) < 0.05 else 0.0
+        table = e.build_table_from_arrays(params, [reads], [nc])
     buf = (ctypes.c_uint64 * 128)()
     e.lib.sonics_debug_ls_stats.argtypes = [ctypes.c_void_p]
-    e.lib.sonics_debug_ls_stats(buf)  # clear
     e.simulate(params, table, n, seed=1)
     e.sync()
+    e.lib.sonics_debug_ls_stats(buf)  # clear
+    import time
+    t0 = time.perf_counter()
+    e.simulate(params, table, n, seed=2)
+    e.sync()
+    ms = (time.perf_counter() - t0) * 1e3
     e.lib.sonics_debug_ls_stats(buf)
+    n = n * table.n_gt
     c = np.array(list(buf), dtype=np.float64)
     nb = c[0]
     d = {
-        "workload": name, "reactions": n, "batches": nb,
+        "workload": name, "reactions": n, "batches": nb, "ms_instrumented": ms,
         "sweep_steps_per_batch": c[13] / nb, "lanes_in_per_sweep_step": c[14] / max(c[13], 1),
         "draw_slots_per_batch": c[1] / nb,
         "slots_by_stage_per_batch": [c[48 + i] / nb for i in range(3)],
