@@ -169,18 +169,20 @@ int sonics_simulate(sonics_ctx *ctx, const SonicsParams *params, const void *dev
  * SONICS_K1=persistent|lockstep sets the initial value of a new ctx (measurement switch). */
 enum { SONICS_KERNEL_AUTO = 0, SONICS_KERNEL_PERSISTENT = 1, SONICS_KERNEL_LOCKSTEP = 2 };
 int sonics_set_kernel(sonics_ctx *ctx, int kernel);
-/* Lockstep form: bits of the sort key spent on the quantised efficiency / down / up priors (each <= 15; eff_bits
+/* Lockstep form, SONICS_SORT_SLOT_MAJOR: bits of the sort key spent on the quantised efficiency / down / up priors (each <= 15; eff_bits
  * < 0 = automatic: about log2(simulations per start-allele group / 32) bits, half of them on the efficiency).  The
  * sort only decides which lane runs which simulation: results never depend on it (tuning knob; env
  * SONICS_SORT_BITS=e,d,u sets the initial value). */
 int sonics_set_sort_bits(sonics_ctx *ctx, int eff_bits, int down_bits, int up_bits);
-/* Lockstep form, launches over many genotypes: which simulations share a warp.
- *   SONICS_SORT_PAIR_MAJOR (default)  noise flag | the two start alleles as absolute repeat counts | priors: a reaction
- *                                     depends on its start alleles and priors, the genotype's reads only enter the
- *                                     lnL, so equal start pairs of ALL genotypes of the launch are pooled (a
- *                                     genotyping round runs 100-400 simulations per genotype, 12-50 per start pair:
- *                                     less than a warp);
- *   SONICS_SORT_SLOT_MAJOR            genotype | start-allele group | priors (what a single-genotype launch uses).
+/* Lockstep form: which simulations share a warp.
+ *   SONICS_SORT_PAIR_MAJOR (default)  noise flag | the two start alleles as absolute repeat counts | reach of the noise
+ *                                     molecules below / above them | the three priors, Morton-interleaved.  A reaction
+ *                                     depends on its start alleles, the noise molecules and its priors; the genotype's
+ *                                     reads only enter the lnL, so like simulations of ALL genotypes of a launch are
+ *                                     pooled (a genotyping round runs 100-400 simulations per genotype, 12-50 per
+ *                                     start pair: less than a warp);
+ *   SONICS_SORT_SLOT_MAJOR            genotype | start-allele group | eff | down | up bit fields
+ *                                     (sonics_set_sort_bits).
  * Results never depend on it (env SONICS_SORT_MODE=pair|slot sets the initial value). */
 enum { SONICS_SORT_PAIR_MAJOR = 0, SONICS_SORT_SLOT_MAJOR = 1 };
 int sonics_set_sort_mode(sonics_ctx *ctx, int mode);

@@ -50,24 +50,26 @@ __shared__ unsigned int s_ls_stats[4][128]; // per warp, written by lane 0, flus
     } while (0)
 #endif
 
-// Sort key of a work unit.
-// pair_major = 0 (one genotype per launch): slot | start-allele group | eff | down | up (quantised priors).
-// pair_major = 1 (many genotypes per launch): what a reaction does depends on its start alleles, the noise molecules
-// and its priors -- the genotype's reads only enter the lnL -- so the 100-400 simulations a genotyping round runs per
-// genotype (12-50 per start-allele group, less than a warp) are pooled with the like simulations of every other
-// genotype of the launch:
+// Sort key of a work unit.  What a reaction does depends on its start alleles, the noise molecules and its priors --
+// the genotype's reads only enter the lnL -- so like simulations are pooled across ALL genotypes of a launch (a
+// genotyping round runs 100-400 simulations per genotype, 12-50 per start-allele group: less than a warp):
+//   pair_major = 1 (default)
 //     noise flag | lower, higher start allele (absolute repeat counts) | reach of the noise below / above them | priors
-// (noise molecules sit on every input allele, sonics.pyx:334-337: with them the live bins of a reaction are the
-// genotype's whole input range; 85 % of the genotypes of a lobSTR-style VCF get them from the automatic rule,
-// sonics:407-416).  The three priors are interleaved bit by bit (Morton order), so any run of 32 neighbours of the
-// sorted list is as compact in (eff, down, up) as the population of its cell allows, whatever that population is.
+//     Noise molecules sit on every input allele (sonics.pyx:334-337): with them the live bins of a reaction are the
+//     genotype's whole input range; 85 % of the genotypes of a lobSTR-style VCF get them from the automatic rule
+//     (sonics:407-416).  The three priors are interleaved bit by bit (Morton order), so any run of 32 neighbours of
+//     the sorted list is as compact in (eff, down, up) as the population of its cell allows, whatever that is.
+//     Measured (B200, profiles/r02_k1_ab.md): cfg4 genotyping 114 k -> 152 k genotypes/s against the genotype-major
+//     key, single-locus launches +4.5 % against eff | down | up bit fields.
+//   pair_major = 0 (sonics_set_sort_mode(SONICS_SORT_SLOT_MAJOR))
+//     genotype slot | start-allele group | eff | down | up as bit fields (sonics_set_sort_bits).
 struct SortCfg {
-    int grp_bits, eff_bits, dn_bits, up_bits, pair_major;
+    int grp_bits, eff_bits, dn_bits, up_bits, pair_major, morton_bits;
 };
 #define SONICS_LS_ALLELE_BITS 9 // SONICS_MAX_ALLELE = 500
 #define SONICS_LS_REACH_BITS 5
-#define SONICS_LS_MORTON_BITS 5 // per prior
-#define SONICS_LS_PAIR_KEY_BITS (1 + 2 * SONICS_LS_ALLELE_BITS + 2 * SONICS_LS_REACH_BITS + 3 * SONICS_LS_MORTON_BITS)
+#define SONICS_LS_MORTON_BITS 5 // per prior (default)
+#define SONICS_LS_PAIR_KEY_BITS(morton_bits) (1 + 2 * SONICS_LS_ALLELE_BITS + 2 * SONICS_LS_REACH_BITS + 3 * (morton_bits))
 
 template <typename KeyT>
 __global__ void k_sort_keys(const SimArgs a, const SortCfg c, KeyT *keys, uint32_t *vals)
@@ -110,10 +112,10 @@ __global__ void k_sort_keys(const SimArgs a, const SortCfg c, KeyT *keys, uint32
         k = (k << SONICS_LS_ALLELE_BITS) | (KeyT)vhi;
         k = (k << SONICS_LS_REACH_BITS) | (KeyT)below;
         k = (k << SONICS_LS_REACH_BITS) | (KeyT)above;
-        const uint32_t qe = quant(pr.eff, a.p.eff_lo, a.p.eff_rng, SONICS_LS_MORTON_BITS);
-        const uint32_t qd = quant(pr.down, a.p.down_lo, a.p.down_rng, SONICS_LS_MORTON_BITS);
-        const uint32_t qu = quant(pr.up, a.p.up_lo, up_rng, SONICS_LS_MORTON_BITS);
-        for (int i = SONICS_LS_MORTON_BITS - 1; i >= 0; --i)
+        const uint32_t qe = quant(pr.eff, a.p.eff_lo, a.p.eff_rng, c.morton_bits);
+        const uint32_t qd = quant(pr.down, a.p.down_lo, a.p.down_rng, c.morton_bits);
+        const uint32_t qu = quant(pr.up, a.p.up_lo, up_rng, c.morton_bits);
+        for (int i = c.morton_bits - 1; i >= 0; --i)
             k = (k << 3) | (KeyT)((((qe >> i) & 1u) << 2) | (((qd >> i) & 1u) << 1) | ((qu >> i) & 1u));
     } else {
         const uint32_t qe = quant(pr.eff, a.p.eff_lo, a.p.eff_rng, c.eff_bits);

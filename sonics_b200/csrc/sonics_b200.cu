@@ -452,8 +452,9 @@ static int launch_simulate_lockstep(sonics_ctx *ctx, SimArgs &a, const TableInfo
     SortCfg sc;
     sc.grp_bits = bits_for(n_groups);
     const int slot_bits = bits_for(n_slots);
-    // many genotypes per launch: pool the simulations of equal start pairs across genotypes (see SortCfg)
-    sc.pair_major = (n_slots > 1 && a.sims_per_gt > 1 && ctx->sort_mode != SONICS_SORT_SLOT_MAJOR) ? 1 : 0;
+    // pool the simulations of equal start pairs across the genotypes of the launch (see SortCfg)
+    sc.pair_major = (a.sims_per_gt > 1 && ctx->sort_mode != SONICS_SORT_SLOT_MAJOR) ? 1 : 0;
+    sc.morton_bits = SONICS_LS_MORTON_BITS;
     const double per_group = (double)a.sims_per_gt / (double)(a.p.random_start ? (int64_t)A * (A + 1) / 2 : A);
     int pbits = 0;
     while (pbits < 15 && per_group / (double)(1 << (pbits + 1)) >= 32.0)
@@ -468,7 +469,7 @@ static int launch_simulate_lockstep(sonics_ctx *ctx, SimArgs &a, const TableInfo
     }
     // one simulation per genotype (K4 replay): the list is already in genotype order
     const int key_bits = a.sims_per_gt == 1 ? 0
-                         : sc.pair_major ? SONICS_LS_PAIR_KEY_BITS
+                         : sc.pair_major ? SONICS_LS_PAIR_KEY_BITS(sc.morton_bits)
                                          : slot_bits + sc.grp_bits + sc.eff_bits + sc.dn_bits + sc.up_bits;
     if (key_bits > 64)
         return fail(SONICS_ERR_RANGE, "sort key of %d bits", key_bits);

@@ -110,7 +110,11 @@ def test_sort_key_bits_do_not_change_results():
     table = e.build_table_from_arrays(p, [orc.parse_reads(CFG2), orc.parse_reads(CFG1)], [0.0, 0.0])
     ref = None
     try:
-        for bits in ((-1, -1, -1), (0, 0, 0), (3, 2, 1), (7, 0, 0), (2, 4, 4), (15, 15, 15)):
+        # the default key (start pair | noise reach | Morton-interleaved priors), then the genotype-major key with
+        # different bit fields
+        for mode, bits in ((0, (-1, -1, -1)), (1, (-1, -1, -1)), (1, (0, 0, 0)), (1, (3, 2, 1)), (1, (7, 0, 0)),
+                           (1, (2, 4, 4)), (1, (15, 15, 15))):
+            check(e.lib.sonics_set_sort_mode(e.ctx, mode))
             check(e.lib.sonics_set_sort_bits(e.ctx, *bits))
             out = e.simulate(p, table, 30000, seed=12, readout=True)
             e.sync()
@@ -120,6 +124,7 @@ def test_sort_key_bits_do_not_change_results():
             _assert_same(ref, got)
     finally:
         check(e.lib.sonics_set_sort_bits(e.ctx, -1, -1, -1))
+        check(e.lib.sonics_set_sort_mode(e.ctx, 0))
 
 
 def test_pair_major_sort_pools_start_pairs_across_genotypes():
