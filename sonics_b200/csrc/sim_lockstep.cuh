@@ -63,13 +63,14 @@ __shared__ unsigned int s_ls_stats[4][128]; // per warp, written by lane 0, flus
 //     key, single-locus launches +4.5 % against eff | down | up bit fields.
 //   pair_major = 0 (sonics_set_sort_mode(SONICS_SORT_SLOT_MAJOR))
 //     genotype slot | start-allele group | eff | down | up as bit fields (sonics_set_sort_bits).
+// The fields are as wide as the table needs (lowest input allele and widest input range of its genotypes, noise
+// present or not), so a single locus sorts 32-bit keys in three radix passes.
 struct SortCfg {
-    int grp_bits, eff_bits, dn_bits, up_bits, pair_major, morton_bits;
+    int grp_bits, eff_bits, dn_bits, up_bits; // slot-major key
+    int pair_major;
+    int al_base, al_bits, span_bits, noise_bits, morton_bits; // pair-major key
 };
-#define SONICS_LS_ALLELE_BITS 9 // SONICS_MAX_ALLELE = 500
-#define SONICS_LS_REACH_BITS 5
-#define SONICS_LS_MORTON_BITS 5 // per prior (default)
-#define SONICS_LS_PAIR_KEY_BITS(morton_bits) (1 + 2 * SONICS_LS_ALLELE_BITS + 2 * SONICS_LS_REACH_BITS + 3 * (morton_bits))
+#define SONICS_LS_MORTON_BITS 5 // per prior
 
 template <typename KeyT>
 __global__ void k_sort_keys(const SimArgs a, const SortCfg c, KeyT *keys, uint32_t *vals)
@@ -104,14 +105,16 @@ __global__ void k_sort_keys(const SimArgs a, const SortCfg c, KeyT *keys, uint32
         const int v1 = a.t.allele[h.a_off + pr.i1], v2 = a.t.allele[h.a_off + pr.i2];
         const int vlo = min(v1, v2), vhi = max(v1, v2);
         const bool noisy = h.noise_add > 0;
-        const int reach_cap = (1 << SONICS_LS_REACH_BITS) - 1;
-        const int below = noisy ? min(vlo - (h.lo + h.in_lo_bin), reach_cap) : 0;
-        const int above = noisy ? min(a.t.allele[h.a_off + h.n_alleles - 1] - vhi, reach_cap) : 0;
-        k = (KeyT)(noisy ? 1 : 0);
-        k = (k << SONICS_LS_ALLELE_BITS) | (KeyT)vlo;
-        k = (k << SONICS_LS_ALLELE_BITS) | (KeyT)vhi;
-        k = (k << SONICS_LS_REACH_BITS) | (KeyT)below;
-        k = (k << SONICS_LS_REACH_BITS) | (KeyT)above;
+        // span_bits hold 0 .. the widest input range of the table: start pair distance and both reaches fit
+        k = (KeyT)(noisy && c.noise_bits ? 1 : 0);
+        k = (k << c.al_bits) | (KeyT)(vlo - c.al_base);
+        k = (k << c.span_bits) | (KeyT)(vhi - vlo);
+        if (c.noise_bits) {
+            const int below = noisy ? vlo - (h.lo + h.in_lo_bin) : 0;
+            const int above = noisy ? a.t.allele[h.a_off + h.n_alleles - 1] - vhi : 0;
+            k = (k << c.span_bits) | (KeyT)below;
+            k = (k << c.span_bits) | (KeyT)above;
+        }
         const uint32_t qe = quant(pr.eff, a.p.eff_lo, a.p.eff_rng, c.morton_bits);
         const uint32_t qd = quant(pr.down, a.p.down_lo, a.p.down_rng, c.morton_bits);
         const uint32_t qu = quant(pr.up, a.p.up_lo, up_rng, c.morton_bits);

@@ -42,6 +42,8 @@ static int fail(int code, const char *fmt, ...)
 
 struct TableInfo {
     int n_gt, n_alleles, max_W, max_A;
+    int min_al, max_al, max_span, any_noise; // lowest / highest input allele, widest input range of a genotype,
+                                             // noise molecules anywhere (lockstep sort key)
     size_t off_allele, off_reads, off_fl;
     std::vector<GtHeader> hdr; // host copy of the headers (the large-n statistics path needs A / first_idx)
 };
@@ -226,7 +228,7 @@ int sonics_table_build(sonics_ctx *ctx, const SonicsParams *params, int n_gt, co
     GtHeader *hdr = (GtHeader *)host.data();
     int32_t *h_allele = (int32_t *)(host.data() + ti.off_allele);
     int32_t *h_reads = (int32_t *)(host.data() + ti.off_reads);
-    int max_W = 0, max_A = 0;
+    int max_W = 0, max_A = 0, min_al = SONICS_MAX_ALLELE, max_al = 0, max_span = 0, any_noise = 0;
     const int64_t sum0 = 2 * (int64_t)((double)params->start_copies / 2.0);
     for (int g = 0; g < n_gt; ++g) {
         const int a0 = allele_off[g], a1 = allele_off[g + 1], A = a1 - a0;
@@ -280,9 +282,17 @@ int sonics_table_build(sonics_ctx *ctx, const SonicsParams *params, int n_gt, co
         h.fl_D = 0.0;
         max_W = std::max(max_W, h.W);
         max_A = std::max(max_A, A);
+        min_al = std::min(min_al, min_in);
+        max_al = std::max(max_al, max_in);
+        max_span = std::max(max_span, max_in - min_in);
+        any_noise |= h.noise_add > 0;
     }
     ti.max_W = max_W;
     ti.max_A = max_A;
+    ti.min_al = min_al;
+    ti.max_al = max_al;
+    ti.max_span = max_span;
+    ti.any_noise = any_noise;
     ti.hdr.assign(hdr, hdr + n_gt);
     CUDA_OK(cudaSetDevice(ctx->device));
     cudaStream_t s = (cudaStream_t)stream;
@@ -454,7 +464,15 @@ static int launch_simulate_lockstep(sonics_ctx *ctx, SimArgs &a, const TableInfo
     const int slot_bits = bits_for(n_slots);
     // pool the simulations of equal start pairs across the genotypes of the launch (see SortCfg)
     sc.pair_major = (a.sims_per_gt > 1 && ctx->sort_mode != SONICS_SORT_SLOT_MAJOR) ? 1 : 0;
+    sc.al_base = ti.min_al;
+    sc.al_bits = bits_for((int64_t)ti.max_al - ti.min_al + 1);
+    sc.span_bits = bits_for((int64_t)ti.max_span + 1);
+    sc.noise_bits = ti.any_noise ? 1 : 0;
     sc.morton_bits = SONICS_LS_MORTON_BITS;
+    const int pair_bits = sc.noise_bits + sc.al_bits + sc.span_bits * (sc.noise_bits ? 3 : 1);
+    // 32-bit keys (8 instead of 12 bytes per unit and pass) when one bit less per prior makes them fit
+    if (pair_bits + 3 * sc.morton_bits > 32 && pair_bits + 3 * (sc.morton_bits - 1) <= 32)
+        sc.morton_bits -= 1;
     const double per_group = (double)a.sims_per_gt / (double)(a.p.random_start ? (int64_t)A * (A + 1) / 2 : A);
     int pbits = 0;
     while (pbits < 15 && per_group / (double)(1 << (pbits + 1)) >= 32.0)
@@ -469,7 +487,7 @@ static int launch_simulate_lockstep(sonics_ctx *ctx, SimArgs &a, const TableInfo
     }
     // one simulation per genotype (K4 replay): the list is already in genotype order
     const int key_bits = a.sims_per_gt == 1 ? 0
-                         : sc.pair_major ? SONICS_LS_PAIR_KEY_BITS(sc.morton_bits)
+                         : sc.pair_major ? pair_bits + 3 * sc.morton_bits
                                          : slot_bits + sc.grp_bits + sc.eff_bits + sc.dn_bits + sc.up_bits;
     if (key_bits > 64)
         return fail(SONICS_ERR_RANGE, "sort key of %d bits", key_bits);
