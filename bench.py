@@ -325,25 +325,22 @@ def genotyping_cpu_baseline(work_items, target_s=15.0):
             "reactions": int(sum(x[1] for x in t)), "seconds": secs}
 
 
-def cfg5_subset_vcf(path, distinct_loci=2500, copies=10, n_samples=32):
-    """cfg5-style input (BASELINE.json configs[4]: coverage 2000-10000, 10 % noisy profiles -> no_success /
-    MWU_test at 1000 repetitions), `copies` x `distinct_loci` loci x 32 samples: the distinct profiles are
-    generated once and written `copies` times under different locus names (different RNG keys), which keeps
-    the generator out of the benchmark's run time."""
+def cfg5_subset_vcf(path, distinct_loci=2500, copies=40, n_samples=32):
+    """cfg5 input (BASELINE.json configs[4]: 100k loci x 32 samples, coverage 2000-10000, 10 % noisy profiles ->
+    no_success / MWU_test at 1000 repetitions) as `copies` x `distinct_loci` loci x 32 samples: the distinct
+    profiles are generated once and written `copies` times under different locus names (different RNG keys),
+    which keeps the generator out of the benchmark's run time."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import synth_vcf
     loci = synth_vcf.make_genotypes(distinct_loci, n_samples, seed=20261019, cov=(2000, 10000), noisy=0.1)
-    tmp = path + ".block"
-    with open(path, "wb") as out:
-        for c in range(copies):
-            synth_vcf.write_vcf(tmp, loci, n_samples, start=c * distinct_loci, header=(c == 0))
-            with open(tmp, "rb") as f:
-                out.write(f.read())
-    os.unlink(tmp)
+    columns = synth_vcf.sample_columns(loci)
+    for c in range(copies):
+        synth_vcf.write_vcf(path, loci, n_samples, start=c * distinct_loci, header=(c == 0), columns=columns,
+                            mode="w" if c == 0 else "a")
     return distinct_loci * copies * n_samples
 
 
-def genotyping_file_to_file(rank, world, barrier, workdir):
+def genotyping_file_to_file(rank, world, barrier, workdir, copies=40):
     """Strong scaling of the genotyping job: one cfg5-style VCF -> sonics_out.txt across all ranks
     (driver.run_sonics under torchrun: round-robin byte pieces, no collective on the data path)."""
     import hashlib
@@ -353,7 +350,7 @@ def genotyping_file_to_file(rank, world, barrier, workdir):
     warm = os.path.join(workdir, "warm.vcf")
     n_gt = 0
     if rank == 0:
-        n_gt = cfg5_subset_vcf(vcf)
+        n_gt = cfg5_subset_vcf(vcf, copies=copies)
         cfg5_subset_vcf(warm, distinct_loci=64, copies=1)
     barrier()
     logging.disable(logging.WARNING)
@@ -379,9 +376,9 @@ def genotyping_file_to_file(rank, world, barrier, workdir):
             rows += blk.count(b"\n")
     return {"value": rows / secs, "unit": "genotypes/s", "n_gpus": world, "seconds": secs, "rows": rows,
             "output_sha256": h.hexdigest(), "scaling": "strong",
-            "workload": "cfg5-style VCF: 25000 loci (2500 distinct profiles x 10) x 32 samples, coverage "
+            "workload": "cfg5 VCF: %d loci (2500 distinct profiles x %d) x 32 samples, coverage "
                         "2000-10000, 10 %% noisy profiles, -r 1000, default filters; VCF file -> sonics_out.txt "
-                        "across %d rank(s), wall clock between barriers" % world,
+                        "across %d rank(s), wall clock between barriers" % (2500 * copies, copies, world),
             "timings_rank0": {k: (round(v, 3) if isinstance(v, float) else v)
                               for k, v in driver.LAST_TIMINGS.items()}}
 
@@ -395,6 +392,9 @@ def main():
     ap.add_argument("--sims", type=int, default=SIMS_PER_STEP, help="reactions per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-genotyping", action="store_true")
+    ap.add_argument("--scaling-copies", type=int, default=40,
+                    help="size of the strong-scaling VCF: 2500 distinct loci x this many copies x 32 samples "
+                         "(40 = BASELINE config 5, 100k loci)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -536,7 +536,7 @@ def main():
             dist.broadcast_object_list(box, src=0)
             workdir = box[0]
         try:
-            geno_scale = genotyping_file_to_file(rank, world, barrier, workdir)
+            geno_scale = genotyping_file_to_file(rank, world, barrier, workdir, args.scaling_copies)
         finally:
             barrier()
             if rank == 0:
@@ -554,6 +554,17 @@ def main():
         achieved_gbs = n * BYTES_PER_REACTION / (kernel_ms * 1e-3) / 1e9
         sm_mhz = clk.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
         peak_issue = 148 * 4 * sm_mhz * 1e6  # warp instructions / s at the clock seen during the run
+        imin = {}
+        pi = os.path.join(ROOT, "profiles", "k1_imin.json")
+        if os.path.exists(pi):
+            imin = json.load(open(pi)).get("per_config", {})
+
+        def algorithmic(rate, peak, name):
+            i = imin.get(name, {}).get("I_min_thread_inst_per_reaction")
+            if not i:
+                return None
+            return {"I_min_thread_inst_per_reaction": i, "frac": i * rate / (peak * 32),
+                    "source": "profiles/k1_imin.json (tests/imin_audit.py)"}
         roof = {"bound": "alu_issue", "achieved": None, "peak": peak_issue, "unit": "warp-inst/s", "frac": None,
                 "traffic": None, "peak_source": "148 SMs x 4 schedulers x SM clock sampled during the run"}
         cnt = load_inst_per_reaction()
@@ -564,12 +575,15 @@ def main():
                 "achieved": ach, "frac": ach / peak_issue,
                 "warp_inst_per_reaction": cnt["warp_inst_per_reaction"],
                 "lanes_active_of_32": cnt.get("avg_active_threads"),
-                # thread-instructions one simulation needs on its own (no idle lanes) against the thread-instruction
-                # peak: reactions/s x I_min / (peak_issue x 32)
-                "achieved_algorithmic": {
-                    "I_min_thread_inst_per_reaction": cnt.get("thread_inst_per_reaction"),
-                    "frac": (cnt.get("thread_inst_per_reaction", 0.0) * n / (kernel_ms * 1e-3)) / (peak_issue * 32),
-                    "per_config": cnt.get("per_config")},
+                # lane-weighted view: thread-instructions executed per reaction (ncu) against the thread-instruction
+                # peak, and the same for the instructions one simulation needs when it runs alone (I_min,
+                # tests/imin_audit.py: the oracle's draw counts priced with this kernel's SASS): reactions/s x I /
+                # (peak_issue x 32)
+                "executed_thread_inst": {
+                    "per_reaction": cnt.get("thread_inst_per_reaction"),
+                    "frac": (cnt.get("thread_inst_per_reaction", 0.0) * n / (kernel_ms * 1e-3)) / (peak_issue * 32)},
+                "achieved_algorithmic": algorithmic(n / (kernel_ms * 1e-3), peak_issue, "cfg2"),
+                "per_config": cnt.get("per_config"),
                 "traffic": cnt.get("dram_bytes_per_reaction", 0.0) * n if cnt.get("dram_bytes_per_reaction") else None,
                 "traffic_note": "DRAM bytes of every kernel of the step (k_sort_keys + radix sort + k_pcr_ls) from "
                                 "ncu, per reaction x reactions of this step",
@@ -599,6 +613,9 @@ def main():
             "sentinel_fraction": frac_sentinel,
             "configs": configs,
         }
+        for name in ("cfg1", "cfg3"):
+            if configs and name in configs:
+                configs[name]["achieved_algorithmic"] = algorithmic(configs[name]["reactions_per_s"], peak_issue, name)
         geno = {}
         items = None
         if world == 1 and not args.no_genotyping:

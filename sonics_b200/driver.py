@@ -76,7 +76,7 @@ def build_parser():
     p.add_argument("--seed", type=int, default=None,
                    help="Philox seed for a reproducible run (default: fresh entropy, like the reference).")
     p.add_argument("--gpus", type=int, default=1, help="GPUs of this box to shard the genotype list over.")
-    p.add_argument("--chunk", type=int, default=65536, help="Genotypes per device batch.")
+    p.add_argument("--chunk", type=int, default=131072, help="Genotypes per device batch.")
     return p
 
 
@@ -218,7 +218,7 @@ def shard_bounds(n, world, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def run_batch_verdicts(allele_off, allele, reads, noise, constants, ranges, options, seed, device=0, chunk=65536,
+def run_batch_verdicts(allele_off, allele, reads, noise, constants, ranges, options, seed, device=0, chunk=131072,
                        uids=None):
     """Verdict array for a CSR batch of genotypes (device batches of `chunk`); uids key the RNG per genotype
     (default: the position in this batch)."""
@@ -331,7 +331,7 @@ def vcf_pipeline(feed_in, byte_range, line_base, out_path, header, constants, op
     return n_rows, n_sim, tm
 
 
-def run_sonics(feed_in, constants, ranges, options, seed=None, gpus=1, chunk=65536):
+def run_sonics(feed_in, constants, ranges, options, seed=None, gpus=1, chunk=131072):
     """run_sonics() of the reference (sonics:160-244) with the genotype loop batched on the GPU(s).
 
     VCF ingest, the pre-filters of process_one_genotype() and the output writer run natively

@@ -53,20 +53,26 @@ def make_genotypes(n_loci, n_samples, seed=20261019, cov=(50, 1000), noisy=0.0):
     return loci
 
 
-def write_vcf(path, loci, n_samples, start=0, header=True):
-    """start: number of loci before these (names / positions continue); header=False: data lines only."""
-    with open(path, "w") as f:
+def sample_columns(loci):
+    """The sample columns of every locus as one string each (what write_vcf renders; reusable across copies)."""
+    out = []
+    for L, R, motif, samples in loci:
+        out.append("\t".join("0/0:" + ";".join("%d|%d" % ((a - R) * L, c) for a, c in reads) for reads in samples))
+    return out
+
+
+def write_vcf(path, loci, n_samples, start=0, header=True, columns=None, mode="w"):
+    """start: number of loci before these (names / positions continue); header=False: data lines only;
+    columns: sample_columns(loci) rendered earlier; mode "a" appends."""
+    columns = columns or sample_columns(loci)
+    with open(path, mode) as f:
         if header:
             f.write("##fileformat=VCFv4.1\n")
             f.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" +
                     "\t".join("sample%d" % (i + 1) for i in range(n_samples)) + "\n")
-        for li, (L, R, motif, samples) in enumerate(loci, start):
-            cols = []
-            for reads in samples:
-                allreads = ";".join("%d|%d" % ((a - R) * L, c) for a, c in reads)
-                cols.append("0/0:" + allreads)
-            f.write("locus%d\t%d\t.\tN\t.\t.\t.\tEND=%d;MOTIF=%s;REF=%d;\tGT:ALLREADS\t%s\n" %
-                    (li + 1, 1000 + li, 1000 + li + L * R, motif, R, "\t".join(cols)))
+        f.write("".join("locus%d\t%d\t.\tN\t.\t.\t.\tEND=%d;MOTIF=%s;REF=%d;\tGT:ALLREADS\t%s\n" %
+                        (li + 1, 1000 + li, 1000 + li + L * R, motif, R, cols)
+                        for (li, (L, R, motif, samples)), cols in zip(enumerate(loci, start), columns)))
 
 
 def genotype_strings(loci):
