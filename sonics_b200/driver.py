@@ -263,6 +263,17 @@ def _verdict_shard_worker(args):
 PIECE_BYTES = 8 << 20  # VCF bytes per pipeline piece (~140 k genotypes of a 32-sample lobSTR file)
 
 
+def even_piece_bytes(size, world):
+    """Piece size for `world` ranks: every rank gets the same number of pieces (a multiple of `world` pieces, at
+    least 8 per rank so that the un-overlapped first parse and last write stay a small share, none above
+    PIECE_BYTES, none below 1 MiB unless the file is that small).  With 22 pieces of 8 MiB on 8 ranks some ranks
+    ran 3 pieces and some 2."""
+    per_rank = max(8, -(-size // (world * PIECE_BYTES)))
+    per_rank = max(1, min(per_rank, size // (world << 20)))  # keep pieces >= 1 MiB
+    n = per_rank * world
+    return max(1, -(-size // n))
+
+
 def vcf_pipeline(feed_in, byte_range, line_base, out_path, header, constants, options, seed, compute,
                  piece_bytes=None, pieces=None, line_bases=None):
     """One process's share of VCF mode, pipelined: the file range is cut into pieces; while the GPU runs
@@ -281,7 +292,9 @@ def vcf_pipeline(feed_in, byte_range, line_base, out_path, header, constants, op
         end = os.path.getsize(feed_in) if hi < 0 else hi
         # pieces small enough that the un-overlapped first parse and last write are a small share of the range
         piece_bytes = piece_bytes or max(1 << 20, min(PIECE_BYTES, (end - lo) // 8))
-        cuts = list(range(lo, end, piece_bytes)) + [end]
+        # a quarter-size first piece: its parse is the one the GPU waits for
+        head = piece_bytes // 4 if end - lo > 2 * piece_bytes else 0
+        cuts = ([lo] if head else []) + list(range(lo + head, end, piece_bytes)) + [end]
         pieces = [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1)]
         if pieces and hi < 0:
             pieces[-1] = (pieces[-1][0], -1)
@@ -423,8 +436,13 @@ def _run_vcf_ranks(feed_in, constants, ranges, options, seed, chunk, out_file_pa
     compute = compute or (lambda off, al, rd, nz, uids: run_batch_verdicts(
         off, al, rd, nz, constants, ranges, options, seed, local, chunk, uids))
     size = os.path.getsize(feed_in)
-    piece_bytes = piece_bytes or max(1 << 20, min(PIECE_BYTES, size // (8 * world)))
-    all_pieces = hostio.pieces_of(feed_in, piece_bytes)
+    if piece_bytes:
+        all_pieces = hostio.pieces_of(feed_in, piece_bytes)
+    else:
+        # every rank starts on a quarter-size piece (its parse is the one the GPU waits for); the rest of the file
+        # in equal pieces, the same number for every rank
+        head = even_piece_bytes(size, world) // 4
+        all_pieces = hostio.pieces_of(feed_in, even_piece_bytes(max(0, size - world * head), world), world, head)
     mine = list(range(rank, len(all_pieces), world))
     gathered = [None] * world
     dist.all_gather_object(gathered, [hostio.count_lines(feed_in, *all_pieces[i]) for i in mine])

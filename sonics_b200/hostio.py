@@ -71,11 +71,20 @@ def count_lines(path, byte_begin, byte_end):
     return n.value
 
 
-def pieces_of(path, piece_bytes):
-    """[begin, end) byte pieces that tile the file (the last one ends at -1 = end of file)."""
+def pieces_of(path, piece_bytes, heads=0, head_bytes=0):
+    """[begin, end) byte pieces that tile the file (the last one ends at -1 = end of file).  heads > 0: the first
+    `heads` pieces are head_bytes long (one short first piece per rank of a round-robin deal: the first parse of a
+    pipeline is the one nothing overlaps)."""
     import os
     size = os.path.getsize(path)
-    cuts = list(range(0, size, max(1, int(piece_bytes)))) + [size]
+    piece_bytes = max(1, int(piece_bytes))
+    cuts = []
+    if heads > 0 and 0 < head_bytes < piece_bytes and heads * head_bytes < size:
+        cuts = [i * int(head_bytes) for i in range(heads)]
+        start = heads * int(head_bytes)
+    else:
+        start = 0
+    cuts += list(range(start, size, piece_bytes)) + [size]
     out = [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1)]
     if out:
         out[-1] = (out[-1][0], -1)
