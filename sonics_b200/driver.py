@@ -464,22 +464,30 @@ def _run_vcf_ranks(feed_in, constants, ranges, options, seed, chunk, out_file_pa
     if not all_pieces:
         sizes = [gathered[0][1][0]]  # header only, written by rank 0
     offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
-    if rank == 0:
-        with open(out_file_path, "wb") as f:
-            f.truncate(int(offs[-1]))
-    dist.barrier()
-    with open(out_file_path, "r+b") as fo, open(part, "rb") as fi:
+    # every rank copies its pieces to their offsets of the output file (writes beyond the end extend it, so nobody
+    # waits for the file to be sized; rank 0 cuts it to its final length -- a longer file of an earlier run -- last)
+    fd_out = os.open(out_file_path, os.O_RDWR | os.O_CREAT, 0o644)
+    fd_in = os.open(part, os.O_RDONLY)
+    try:
+        src = 0
         for j, i in enumerate(mine if all_pieces else ([0] if rank == 0 else [])):
-            fo.seek(int(offs[i]))
-            left = sizes[i]
+            dst, left = int(offs[i]), int(sizes[i])
             while left > 0:
-                buf = fi.read(min(left, 8 << 20))
-                if not buf:
+                try:
+                    n = os.copy_file_range(fd_in, fd_out, left, src, dst)  # in-kernel copy, same file system
+                except (OSError, AttributeError):
+                    buf = os.pread(fd_in, min(left, 8 << 20), src)
+                    n = os.pwrite(fd_out, buf, dst) if buf else 0
+                if n <= 0:
                     break
-                fo.write(buf)
-                left -= len(buf)
+                src, dst, left = src + n, dst + n, left - n
+    finally:
+        os.close(fd_in)
+        os.close(fd_out)
     os.unlink(part)
     dist.barrier()
+    if rank == 0:
+        os.truncate(out_file_path, int(offs[-1]))
     LAST_TIMINGS.clear()
     tm.pop("row_bytes", None)
     LAST_TIMINGS.update(tm, join=time.time() - t1, genotypes=n_sim, wall=time.time() - t0, pieces_total=len(all_pieces))

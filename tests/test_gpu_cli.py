@@ -155,6 +155,8 @@ def test_concordance_at_baseline_scale(name, n_loci, n_samples, cov, noisy):
     from sonics_b200 import engine as eng
     from sonics_b200.sonics import filter_string
     from tests.gpu_util import engine
+    # SONICS_CONCORDANCE_SCALE=k: k times as many loci (a one-off larger run, report kept under profiles/)
+    n_loci *= int(os.environ.get("SONICS_CONCORDANCE_SCALE", "1"))
     loci = synth_vcf.make_genotypes(n_loci, n_samples, seed=20261019, cov=cov, noisy=noisy)
     constants = {"one_allele_threshold": 45, "noise_threshold": 0.05}
     work = [p for k, p in (driver.prefilter(t, constants, {"monte_carlo": False})
