@@ -11,8 +11,9 @@ Under torchrun (N > 1) every rank simulates its own disjoint range of simulation
 same locus (weak scaling, no collective on the data path); rank 0 prints ONE JSON line.
 
   value  simulated PCR reactions/s, whole job, inputs resident in HBM, CUDA-event timed
-  e2e    same metric through the public host API (genotype string in host memory -> table build
-         + H2D -> simulate -> lnL/group arrays copied back to pinned host memory)
+  e2e    same metric through the public host API as a stream of jobs (genotype string in host memory -> table
+         build + H2D -> simulate -> lnL/group arrays copied back to pinned host memory; the copy of step i overlaps
+         the simulation of step i + 1, all copies inside the timed region)
   roofline        the bounding roofline: warp instructions issued per second against
                   148 SMs x 4 schedulers x SM clock.  Instructions per reaction come from the committed ncu
                   capture (profiles/k1_counters.json, guarded by a hash of the kernel sources: a stale file
@@ -435,20 +436,45 @@ def main():
         # every rank owns the simulation indices [rank*n, (rank+1)*n) of step i's seed
         return e.simulate(params, table, n, seed=20261019 + i, sim_begin=rank * n, out_offset=0, out=out)
 
+    # end to end through the public host API, as a stream of jobs: genotype string in host memory -> table build +
+    # H2D -> simulate -> lnL / group copied to pinned host memory.  The device-to-host copy of step i runs on its own
+    # stream while step i + 1 computes (two result buffers on either side of PCIe); every step's copies lie inside
+    # the timed region, which ends when the last one has landed.
+    copy_stream = torch.cuda.Stream(device=dev)
+    e2e_out = [out, {k: torch.empty_like(v) for k, v in out.items()}]
+    e2e_host = [(h_lnL, h_grp), (torch.empty((1, n), dtype=torch.float64, pin_memory=True),
+                                 torch.empty((1, n), dtype=torch.int16, pin_memory=True))]
+    e2e_copied = [None, None]
+    e2e_tables = []
+
     def e2e_step(i):
-        # public host API: genotype string in host memory -> ... -> lnL/group on the host
+        k = i & 1
         al, _, _ = drop_in.get_alleles(CFG2)
         t = e.build_table_from_arrays(params, [al], [0.0], uid=[0])
-        o = e.simulate(params, t, n, seed=777 + i, sim_begin=rank * n, out_offset=0, out=out)
-        h_lnL.copy_(o["lnL"], non_blocking=True)
-        h_grp.copy_(o["group"], non_blocking=True)
-        torch.cuda.synchronize()
+        e2e_tables.append(t)
+        if e2e_copied[k] is not None:  # the copy of step i - 2 has left this result buffer
+            torch.cuda.current_stream().wait_event(e2e_copied[k])
+        o = e.simulate(params, t, n, seed=777 + i, sim_begin=rank * n, out_offset=0, out=e2e_out[k])
+        done = torch.cuda.Event()
+        done.record()
+        copy_stream.wait_event(done)
+        with torch.cuda.stream(copy_stream):
+            e2e_host[k][0].copy_(o["lnL"], non_blocking=True)
+            e2e_host[k][1].copy_(o["group"], non_blocking=True)
+            e2e_copied[k] = torch.cuda.Event()
+            e2e_copied[k].record(copy_stream)
         return t
+
+    def e2e_drain():
+        copy_stream.synchronize()
+        torch.cuda.synchronize()
+        del e2e_tables[:-1]
 
     # ---- warm-up ----
     for i in range(max(3, args.warmup)):
         dev_step(-1 - i)
     e2e_step(-1)
+    e2e_drain()
     barrier()
 
     # ---- device-resident timing: K steps, CUDA events on the launching stream, L2 flushed between steps ----
@@ -474,13 +500,14 @@ def main():
     t0 = time.perf_counter()
     for i in range(args.steps):
         tbl = e2e_step(i)
+    e2e_drain()
     barrier()
     e2e_s = time.perf_counter() - t0
     h2d = int(tbl.buf.numel())
     d2h = int(h_lnL.numel() * 8 + h_grp.numel() * 2)
 
     # sanity: the work was really done (sentinel fraction and group spread of the last step)
-    lnl_host = h_lnL.numpy()[0]
+    lnl_host = e2e_host[(args.steps - 1) & 1][0].numpy()[0]
     frac_sentinel = float((lnl_host == -999999.0).mean())
     assert 0.05 < frac_sentinel < 0.5 and np.isfinite(lnl_host).all(), frac_sentinel
 

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsonics_b200.so")
 SOURCES = ["sonics_b200.cu"]
-DEPS = ["sonics_b200.cu", "sim_kernel.cuh", "sim_lockstep.cuh", "finish.cuh", "stats_kernel.cuh", "stats_big.cuh", "abi_stats.inl", "host_io.inl", "samplers.cuh", "rng.cuh", "lnl.cuh",
+DEPS = ["sonics_b200.cu", "sim_kernel.cuh", "sim_lockstep.cuh", "finish.cuh", "stats_kernel.cuh", "abi_stats.inl", "host_io.inl", "samplers.cuh", "rng.cuh", "lnl.cuh",
         os.path.join("..", "..", "include", "sonics_b200.h")]
 
 NVCC_FLAGS = [

@@ -1,5 +1,7 @@
 // extern "C" entry points for the statistics / repeat-until-pass path (included by sonics_b200.cu).
 
+static size_t big_align(size_t v) { return (v + 255) & ~(size_t)255; }
+
 static int next_pow2(int v)
 {
     int p = 1;
@@ -184,134 +186,6 @@ static int launch_evaluate_global(sonics_ctx *ctx, EvalArgs a, int n_active, int
     return SONICS_OK;
 }
 
-struct SlotIsN { // indicator "sorted element i belongs to the target slot", 0 for the closing index n
-    const uint16_t *slot;
-    const BigState *st;
-    int fixed; // >= 0: fixed target; -1: st->best; -2: st->second
-    int n;
-    __device__ uint32_t operator()(uint32_t i) const
-    {
-        if ((int)i >= n)
-            return 0u;
-        const int target = fixed >= 0 ? fixed : (fixed == -1 ? st->best : st->second);
-        return slot[i] == target ? 1u : 0u;
-    }
-};
-
-// Statistics of ONE genotype with n_run > SONICS_STATS_MAX_N simulations (see stats_big.cuh).
-static int evaluate_big_one(sonics_ctx *ctx, const EvalArgs &a, const TableInfo &ti, int g, void *scratch,
-                            size_t scratch_bytes, cudaStream_t s)
-{
-    const int n = a.n_run;
-    const GtHeader &h = ti.hdr[g];
-    const int A = h.n_alleles;
-    const int n_slots = a.random_start ? A * A : A;
-    if (scratch_bytes < stats_big_bytes(n, n_slots))
-        return fail(SONICS_ERR_SPACE, "statistics scratch %zu < %zu bytes for %d simulations per genotype", scratch_bytes,
-                    stats_big_bytes(n, n_slots), n);
-    const int64_t base = (int64_t)g * a.out_stride;
-    unsigned char *p = (unsigned char *)scratch;
-    BigBufs b;
-    auto take = [&](size_t bytes) {
-        void *r = p;
-        p += big_align(bytes);
-        return r;
-    };
-    b.keys = (double *)take((size_t)n * 8);
-    b.idx = (uint32_t *)take((size_t)n * 4);
-    b.idx_in = (uint32_t *)take((size_t)n * 4);
-    b.slot = (uint16_t *)take((size_t)n * 2);
-    b.flag = (unsigned char *)take((size_t)n);
-    b.heads = (uint32_t *)take((size_t)(n + 1) * 4);
-    b.S_best = (uint32_t *)take((size_t)(n + 1) * 4);
-    b.S = (uint32_t *)take((size_t)(n + 1) * 4);
-    b.tmp_in = (double *)take((size_t)n * 8);
-    b.tmp_out = (double *)take((size_t)n * 8);
-    b.cnt = (int *)take((size_t)n_slots * 4);
-    b.cnt_valid = (int *)take((size_t)n_slots * 4);
-    b.maxk = (unsigned long long *)take((size_t)n_slots * 8);
-    b.st = (BigState *)take(sizeof(BigState));
-    b.cub_tmp = p;
-    b.cub_bytes = scratch_bytes - (size_t)(p - (unsigned char *)scratch);
-    const int T = 256, nb = (n + T - 1) / T, nbs = std::min(nb, ctx->sm_count * 8);
-    int *n_heads_dev = &b.st->pad; // DeviceSelect writes the number of run heads here
-
-    k_big_init<<<std::max(nb, (n_slots + T - 1) / T), T, 0, s>>>(b, n, n_slots);
-    ctx->launches++;
-    size_t need = 0;
-    CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, need, a.lnL + base, b.keys, b.idx_in, b.idx, n, 0, 64, s));
-    if (need > b.cub_bytes)
-        return fail(SONICS_ERR_SPACE, "CUB sort needs %zu bytes of temporary storage, %zu available", need, b.cub_bytes);
-    need = b.cub_bytes;
-    CUDA_OK(cub::DeviceRadixSort::SortPairs(b.cub_tmp, need, a.lnL + base, b.keys, b.idx_in, b.idx, n, 0, 64, s));
-    ctx->launches++;
-    k_big_slots<<<nb, T, 0, s>>>(b, a.group + base, n, A, h.first_idx, a.random_start);
-    ctx->launches++;
-    cub::CountingInputIterator<uint32_t> iota(0u);
-    need = b.cub_bytes;
-    CUDA_OK(cub::DeviceSelect::Flagged(b.cub_tmp, need, iota, b.flag, b.heads, n_heads_dev, n, s));
-    ctx->launches++;
-    k_big_top2<<<1, 1, 0, s>>>(b, n, n_slots, a.min_sim_opt, n_heads_dev);
-    ctx->launches++;
-
-    auto scan = [&](int fixed, uint32_t *out) -> int {
-        SlotIsN f{b.slot, b.st, fixed, n};
-        cub::TransformInputIterator<uint32_t, SlotIsN, cub::CountingInputIterator<uint32_t>> it(iota, f);
-        size_t nb2 = b.cub_bytes;
-        CUDA_OK(cub::DeviceScan::ExclusiveSum(b.cub_tmp, nb2, it, out, n + 1, s));
-        ctx->launches++;
-        return SONICS_OK;
-    };
-
-    if (a.monte_carlo) {
-        k_big_best_row<<<1, 256, 0, s>>>(b, n, 1);
-        k_big_set_best_slot<<<1, 1, 0, s>>>(b, a.group, base, A, h.first_idx, a.random_start);
-        ctx->launches += 2;
-        if (int rc = scan(-1, b.S_best))
-            return rc;
-        k_big_pick<<<nbs, T, 0, s>>>(b, b.S_best, n, 0, 0.75, 0);
-        ctx->launches++;
-        for (int which = 0; which < 2; ++which) {
-            k_big_gather<<<nb, T, 0, s>>>(b, a.group, a.identity, a.rsq, base, n, A, h.first_idx, a.random_start, which);
-            need = b.cub_bytes;
-            CUDA_OK(cub::DeviceRadixSort::SortKeys(b.cub_tmp, need, b.tmp_in, b.tmp_out, n, 0, 64, s));
-            k_big_q75_sorted<<<1, 1, 0, s>>>(b, which);
-            ctx->launches += 3;
-        }
-        k_big_verdict<<<1, 1, 0, s>>>(b, a, g, n);
-        ctx->launches++;
-        CUDA_OK(cudaGetLastError());
-        return SONICS_OK;
-    }
-
-    k_big_best_row<<<1, 256, 0, s>>>(b, n, 0);
-    ctx->launches++;
-    if (int rc = scan(-1, b.S_best))
-        return rc;
-    if (int rc = scan(-2, b.S))
-        return rc;
-    for (int qi = 0; qi <= a.n_add; ++qi) {
-        const double q = qi == 0 ? 0.75 : a.add_q[qi - 1];
-        k_big_pick<<<nbs, T, 0, s>>>(b, b.S_best, n, 0, q, 0);
-        k_big_pick<<<nbs, T, 0, s>>>(b, b.S, n, 1, q, 2);
-        k_big_ratio<<<1, 1, 0, s>>>(b, q, qi - 1);
-        ctx->launches += 3;
-    }
-    for (int t = 0; t < n_slots; ++t) {
-        k_big_pair_begin<<<1, 1, 0, s>>>(b);
-        ctx->launches++;
-        if (int rc = scan(t, b.S))
-            return rc;
-        k_big_pair<<<nbs, T, 0, s>>>(b, t);
-        k_big_pair_end<<<1, 1, 0, s>>>(b, t);
-        ctx->launches += 2;
-    }
-    k_big_verdict<<<1, 1, 0, s>>>(b, a, g, n);
-    ctx->launches++;
-    CUDA_OK(cudaGetLastError());
-    return SONICS_OK;
-}
-
 static int launch_evaluate(sonics_ctx *ctx, const SonicsParams *params, const TableInfo &ti, const TableView &tv,
                            const int32_t *dev_active, int n_active, int64_t n_run, int64_t out_stride,
                            const double *dev_lnL, const uint16_t *dev_group, const double *dev_identity,
@@ -337,29 +211,8 @@ static int launch_evaluate(sonics_ctx *ctx, const SonicsParams *params, const Ta
     }
     // more simulations per genotype than shared memory holds (-r above 8192), or more start-allele groups
     // (--random with more than 45 alleles): the same kernel over global-memory arrays sorted by CUB, many
-    // genotypes per launch
-    if (!params->monte_carlo)
-        return launch_evaluate_global(ctx, a, n_active, n_slots, dev_scratch, dev_scratch_bytes, s);
-    if (n_slots > SONICS_STATS_MAX_SLOTS)
-        return fail(SONICS_ERR_RANGE, "--monte_carlo with %d genotype groups: at most %d are supported in this mode "
-                                      "(use fewer alleles with --random)", n_slots, SONICS_STATS_MAX_SLOTS);
-    // --monte_carlo with a large -r: one genotype at a time (a single locus is the typical use)
-    if (!dev_scratch)
-        return fail(SONICS_ERR_SPACE, "statistics over %lld simulations per genotype need a scratch buffer of "
-                                      "sonics_stats_scratch_bytes() bytes",
-                    (long long)n_run);
-    std::vector<int32_t> act(n_active);
-    if (dev_active) {
-        CUDA_OK(cudaMemcpyAsync(act.data(), dev_active, (size_t)n_active * 4, cudaMemcpyDeviceToHost, s));
-        CUDA_OK(cudaStreamSynchronize(s));
-    } else {
-        for (int i = 0; i < n_active; ++i)
-            act[i] = i;
-    }
-    for (int i = 0; i < n_active; ++i)
-        if (int rc = evaluate_big_one(ctx, a, ti, act[i], dev_scratch, dev_scratch_bytes, s))
-            return rc;
-    return SONICS_OK;
+    // genotypes per launch, both modes
+    return launch_evaluate_global(ctx, a, n_active, n_slots, dev_scratch, dev_scratch_bytes, s);
 }
 
 extern "C" {
@@ -369,13 +222,10 @@ size_t sonics_stats_scratch_bytes_batch(int n_active, int64_t n_run, int max_all
     const int n_slots = random_start ? max_alleles * max_alleles : max_alleles;
     if ((n_run <= SONICS_STATS_MAX_N && n_slots <= SONICS_STATS_MAX_SLOTS) || n_run <= 0 || n_active <= 0)
         return 0;
-    // default mode: all genotypes in one chunk; --monte_carlo: one genotype at a time through stats_big.cuh
+    // all genotypes in one chunk (anything from the size for one genotype up works: more chunks)
     const int64_t c = std::max<int64_t>(1, std::min<int64_t>(n_active, ((int64_t)1 << 31) / (n_run + 1) - 1));
     GlobalLayout L;
-    size_t b = global_layout(c, n_run, n_slots, L) == 0 ? L.total : 0;
-    if (n_slots <= SONICS_STATS_MAX_SLOTS)
-        b = std::max(b, stats_big_bytes(n_run, n_slots));
-    return b;
+    return global_layout(c, n_run, n_slots, L) == 0 ? L.total : 0;
 }
 
 size_t sonics_stats_scratch_bytes(int64_t n_run, int max_alleles, int random_start)
@@ -502,8 +352,6 @@ static BatchLayout batch_layout(int n_gt, int n_alleles_total, int max_reps, int
             one = g1.total;
         if (global_layout(c, max_reps, ns, gall) == 0)
             all = gall.total;
-        if (ns <= SONICS_STATS_MAX_SLOTS && max_reps > SONICS_STATS_MAX_N)
-            one = std::max(one, stats_big_bytes(max_reps, ns)); // --monte_carlo keeps the one-at-a-time path
         L.scratch_bytes = std::max(L.scratch_bytes, std::max(one, std::min<size_t>(all, (size_t)8 << 30)));
     }
     o += align_up(L.scratch_bytes, 256);

@@ -12,11 +12,12 @@
 #include <string>
 #include <vector>
 
+#include <cub/cub.cuh>
+
 #include "../../include/sonics_b200.h"
 #include "sim_kernel.cuh"
 #include "sim_lockstep.cuh"
 #include "stats_kernel.cuh"
-#include "stats_big.cuh"
 
 using namespace sonics;
 

@@ -278,6 +278,45 @@ __device__ __forceinline__ void tie_blocks_global(const unsigned long long *key,
     __syncthreads();
 }
 
+// k-th smallest (0-based) of the keys key_of(i), i in [0, n) with member(i): an 8-pass MSD radix select, the
+// histogram of one byte per pass in shared memory (hist: 256 words, sh: 2 ints).  No sort, no scratch: the q75 of the
+// identity / r^2 column of the best group in --monte_carlo mode when the simulations live in global memory.
+template <typename Member, typename KeyOf>
+__device__ __forceinline__ unsigned long long radix_select(Member member, KeyOf key_of, int n, int k,
+                                                           unsigned int *hist, int *sh)
+{
+    unsigned long long prefix = 0ull, mask = 0ull;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x)
+            hist[i] = 0u;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            if (!member(i))
+                continue;
+            const unsigned long long key = key_of(i);
+            if ((key & mask) == prefix)
+                atomicAdd(&hist[(unsigned int)(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int cum = 0, b = 0;
+            for (; b < 255; ++b) {
+                if (cum + (int)hist[b] > k)
+                    break;
+                cum += (int)hist[b];
+            }
+            sh[0] = b;
+            sh[1] = k - cum;
+        }
+        __syncthreads();
+        prefix |= (unsigned long long)sh[0] << shift;
+        mask |= 0xffull << shift;
+        k = sh[1];
+        __syncthreads();
+    }
+    return prefix;
+}
+
 __device__ __forceinline__ int slot_of(int gid, int A, int first_idx, int random_start)
 {
     if (random_start)
@@ -289,8 +328,8 @@ __device__ __forceinline__ int slot_of(int gid, int A, int first_idx, int random
 // BIG = false: everything in shared memory (n_run <= SONICS_STATS_MAX_N, groups <= SONICS_STATS_MAX_SLOTS), the sort
 //               included (bitonic).
 // BIG = true:  the per-simulation arrays live in global memory (EvalArgs::g_*), already sorted by CUB; the group
-//              counters stay in shared memory when they fit (smem_slots != 0).  Default mode only: the --monte_carlo
-//              branch needs two more sorts and keeps its own path (stats_big.cuh).
+//              counters stay in shared memory when they fit (smem_slots != 0).  The --monte_carlo branch takes the
+//              q75 of the identity / r^2 columns with a radix select instead of two more sorts.
 template <bool BIG>
 __global__ void __launch_bounds__(BIG ? 1024 : SONICS_STATS_THREADS) k_evaluate_t(const EvalArgs a, int n_slots_cap,
                                                                                   int smem_slots)
@@ -446,7 +485,7 @@ __global__ void __launch_bounds__(BIG ? 1024 : SONICS_STATS_THREADS) k_evaluate_
     v.n_groups = G;
     v.min_sim = min_sim;
 
-    if (!BIG && a.monte_carlo) {
+    if (a.monte_carlo) {
         // ---- MC mode (:115-131): best row = global max lnL; q75 of ident, r^2, lnL within its group ----
         const int gbest = m.slot[n - 1];
         // the reported row: lowest simulation index among the rows tied at the maximum
@@ -479,7 +518,18 @@ __global__ void __launch_bounds__(BIG ? 1024 : SONICS_STATS_THREADS) k_evaluate_
         const double lnL_q75 = lerp_np(sh_d[0], sh_d[1], tq);
         __syncthreads();
         double q_extra[2] = {0.0, 0.0};
-        for (int which = 0; which < 2; ++which) {
+        for (int which = 0; which < 2 && BIG; ++which) {
+            __shared__ unsigned int sh_hist[256];
+            auto member = [&](int i) { return slot_of(a.group[base + i], A, h.first_idx, a.random_start) == gslot; };
+            auto key_of = [&](int i) {
+                return f64_key(which == 0 ? (a.identity ? a.identity[base + i] : 0.0)
+                                          : (a.rsq ? (double)a.rsq[base + i] : 0.0));
+            };
+            const double lo_v = key_f64(radix_select(member, key_of, n, k0, sh_hist, sh_i + 5));
+            const double hi_v = k1 == k0 ? lo_v : key_f64(radix_select(member, key_of, n, k1, sh_hist, sh_i + 5));
+            q_extra[which] = lerp_np(lo_v, hi_v, tq);
+        }
+        for (int which = 0; which < 2 && !BIG; ++which) {
             // sort the group's identity (which = 0) / r^2 (which = 1) values; everything else -> +inf
             for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
                 unsigned long long k = 0xffffffffffffffffull;

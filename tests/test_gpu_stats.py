@@ -460,3 +460,47 @@ def test_random_start_with_more_groups_than_shared_memory_holds():
     off, al, rd = eng.to_csr(arrays[:1])
     w = e.genotype_batch(params, off, al, rd, [0.003], 1000, seed=42)
     assert w[0]["run_reps"] == 1000 and w[0]["n_groups"] > 300
+
+
+def _check_mc_verdict(v, table, g, lnL, grp, ident, rsq):
+    bi = int(np.argmax(lnL))   # first occurrence of the maximum (sonics.pyx:115-117)
+    assert v["best_sim"] == bi and v["lnL"] == lnL[bi] and v["identity"] == ident[bi] and v["r_squared"] == rsq[bi]
+    m = grp == grp[bi]
+    assert table.group_label(g, int(grp[bi])) == "%d/%d" % (v["allele_lo"], v["allele_hi"])
+    assert v["lnL_q75"] == stats.quantile_linear(np.sort(lnL[m]), 0.75)
+    assert v["identity_q75"] == stats.quantile_linear(np.sort(ident[m]), 0.75)
+    assert v["r_squared_q75"] == stats.quantile_linear(np.sort(rsq[m]), 0.75)
+
+
+@pytest.mark.parametrize("n_run", [8192, 8193, 30000])
+def test_monte_carlo_mode_over_global_memory_many_genotypes(n_run):
+    """--monte_carlo rows (sonics.pyx:115-134) for several genotypes in one launch on both sides of the on-chip limit:
+    the q75 of the identity / r^2 columns of the best group comes from two bitonic sorts on chip and from a radix
+    select over global memory; both must equal numpy's linear quantile of the same arrays."""
+    e = engine()
+    params = eng.make_params(monte_carlo=True)
+    gts = [CFG1, CFG2, "14|700;15|2100;16|1900;17|2500;18|900;19|300", "9|100;10|100", "9|2;10|3;11|2", CFG1]
+    arrays = [orc.parse_reads(g) for g in gts]
+    table = e.build_table_from_arrays(params, arrays, [orc.auto_noise_coef(a) for a in arrays],
+                                      uid=list(range(70, 70 + len(gts))))
+    out = e.simulate(params, table, n_run, seed=51, readout=True)
+    v = e.verdicts_to_host(e.evaluate(params, table, out, n_run, final_round=True))
+    for g in range(len(gts)):
+        _check_mc_verdict(v[g], table, g, out["lnL"][g].cpu().numpy(),
+                          out["group"][g].cpu().numpy().view(np.uint16), out["identity"][g].cpu().numpy(),
+                          out["rsq"][g].cpu().numpy().astype(np.float64))
+        assert v[g]["run_reps"] == n_run
+
+
+def test_monte_carlo_mode_with_more_groups_than_shared_memory_holds():
+    """--monte_carlo --random with 51 input alleles (2601 group slots): rejected in round 1, now the global-memory
+    form."""
+    e = engine()
+    params = eng.make_params(monte_carlo=True, random=True, n_cycles=8, capture_cycle=5)
+    wide = ";".join("%d|%d" % (a, 30 + 5 * ((a * 7) % 11)) for a in range(10, 61))
+    table = e.build_table_from_arrays(params, [orc.parse_reads(wide)], [0.003])
+    n = 60000
+    out = e.simulate(params, table, n, seed=52, readout=True)
+    v = e.verdicts_to_host(e.evaluate(params, table, out, n, final_round=True))[0]
+    _check_mc_verdict(v, table, 0, out["lnL"][0].cpu().numpy(), out["group"][0].cpu().numpy().view(np.uint16),
+                      out["identity"][0].cpu().numpy(), out["rsq"][0].cpu().numpy().astype(np.float64))
