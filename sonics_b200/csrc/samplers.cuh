@@ -4,7 +4,7 @@
 // sonics.pyx:354,454,458,462,478 and np.random.poisson (PTRS) at :420.  Those
 // are rejection / inversion samplers of the exact distributions; here the same
 // distributions are sampled with algorithms that map better onto SIMT lanes:
-//   binomial:  n*min(p,1-p) < 10  -> sequential inversion from 0 (BINV)
+//   binomial:  n*min(p,1-p) < 20  -> sequential inversion from 0 (BINV)
 //              otherwise          -> BTRS transformed rejection (Hoermann, "The generation of
 //                                    binomial random variates", J. Stat. Comput. Simul. 46, 1993)
 //                                    with the squeeze of BTPE (Kachitvichyanukul & Schmeiser,
@@ -31,6 +31,13 @@
 namespace sonics {
 
 #define SONICS_RCP_TABLE 192 // 1/x for x in [0, 192) (inversion recurrences; index 0 unused)
+// Binomial(n, p): sequential inversion below this n min(p, q), BTRS from it on (BTRS needs >= 10; numpy switches at
+// 30).  In lockstep a BTRS slot costs ~77 instructions of set-up + 2.6 rejection rounds of ~95, an inversion slot
+// ~80 + 9 per step of its slowest lane: measured on B200 (profiles/r02_k1_ab.md) 10 -> 17 -> 20 -> 24 -> 30 -> 40 gives
+// cfg2 1.089 -> 1.130 -> 1.133 -> 1.133 -> 1.131 -> 1.116e8 reactions/s (with the pinned histogram address).
+#ifndef SONICS_INV_BELOW
+#define SONICS_INV_BELOW 20.0f
+#endif
 
 // Single-instruction MUFU approximations.  __fdividef / __logf / sqrtf wrap the same units in range scaling
 // for denormal and huge operands (5-8 instructions each; the BTRS quick path is ~17 instructions long and
@@ -82,19 +89,19 @@ struct DrawState {
     int ix, icap;
 };
 
-// ---- inversion: Binomial(n, p), p <= 0.5, n*p < 10 ----
+// ---- inversion: Binomial(n, p), p <= 0.5, n*p < SONICS_INV_BELOW ----
 __device__ __forceinline__ void inv_setup(DrawState &v, int n, float p)
 {
     const float q = 1.0f - p;
     v.b = p * rcp_fast(q);
     v.a = (float)(n + 1) * v.b;
     v.A = __expf((float)n * log1pf(-p)); // px = q^n
-    v.icap = n < SONICS_RCP_TABLE - 1 ? n : SONICS_RCP_TABLE - 1; // P(X > 160 | np < 10) < 1e-130
+    v.icap = n < SONICS_RCP_TABLE - 1 ? n : SONICS_RCP_TABLE - 1; // P(X > 190 | np < 20) < 1e-100
     v.ix = 0;
     v.fk = 0.0f;
 }
 __device__ __forceinline__ void inv_start(DrawState &v, uint32_t bits) { v.fk = u01_fine(bits); }
-// the sequential search, to its end (at most icap < SONICS_RCP_TABLE steps; n*p < 10 makes ~2 typical):
+// the sequential search, to its end (at most icap < SONICS_RCP_TABLE steps; n*p < 20: a handful typical):
 // result v.ix.  No step counter and a running table pointer: the loop runs with ~3 lanes, so every
 // instruction in it is paid ten times over.
 __device__ __forceinline__ void inv_run(DrawState &v, const float *rcp_tab)
@@ -270,7 +277,7 @@ __device__ __forceinline__ int binomial(Rng &rng, int n, float p, uint32_t bits_
     const float pp = flip ? 1.0f - p : p;
     DrawState s;
     int k;
-    if ((float)n * pp < 10.0f) {
+    if ((float)n * pp < SONICS_INV_BELOW) {
         inv_setup(s, n, pp);
         inv_start(s, bits_a);
         inv_run(s, rcp_tab);

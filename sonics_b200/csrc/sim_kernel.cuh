@@ -31,7 +31,7 @@
 //   * each lane runs its simulation as a small state machine and the warp iterates over "passes";
 //     in one pass a lane performs ADVANCE when its draw has finished and then at most one of
 //       ADVANCE  consume the finished draw, walk the sweep to the next draw, set it up
-//       INV      set-up + the whole sequential-search inversion      (n*min(p,q) < 10) -- run when
+//       INV      set-up + the whole sequential-search inversion      (n*min(p,q) < 20) -- run when
 //                >= 6 lanes wait for it
 //       BTRS     one transformed-rejection trial incl. squeeze        (otherwise)
 //       POIS     one PTRS trial / the small-lambda inversion          (capture step)
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(128, SONICS_PCR_MIN_BLOCKS) k_pcr(const SimArg
                 } else {
                     flip = dp > 0.5f;
                     const float pp = flip ? 1.0f - dp : dp;
-                    if ((float)dn * pp < 10.0f) {
+                    if ((float)dn * pp < SONICS_INV_BELOW) {
                         ds.p = pp; // set up when the INV phase runs
                         mode = M_INV0;
                     } else {

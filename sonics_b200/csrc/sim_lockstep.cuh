@@ -147,7 +147,7 @@ __device__ __forceinline__ int binomial_ls(PairRng &rng, int n, float p, const f
     }
     const bool flip = p > 0.5f;
     const float pp = flip ? 1.0f - p : p;
-    const bool inv = need && (float)n * pp < 10.0f;
+    const bool inv = need && (float)n * pp < SONICS_INV_BELOW;
     bool pend = need && !inv;
     int guard = 0;
     DrawState ds;
@@ -255,6 +255,17 @@ __device__ __forceinline__ int poisson_ls(PairRng &rng, bool need, float lam)
 }
 
 // Shared memory: [rcp table][warp 0 hist: Wcap x 32 int32][warp 1 hist]...   (same as k_pcr)
+__device__ __forceinline__ int lds_u32(uint32_t addr)
+{
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, int v)
+{
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 template <bool READOUT>
 __global__ void __launch_bounds__(128, SONICS_LS_MIN_BLOCKS) k_pcr_ls(const SimArgs a)
 {
@@ -271,6 +282,12 @@ __global__ void __launch_bounds__(128, SONICS_LS_MIN_BLOCKS) k_pcr_ls(const SimA
 #endif
     __syncthreads();
     int *hist = reinterpret_cast<int *>(smem_raw + SONICS_RCP_TABLE * 4 + (size_t)warp * warp_smem_bytes(Wcap)) + lane;
+    // the sweep addresses its column through one 32-bit shared-memory address that the compiler cannot rebuild from
+    // threadIdx at every bin (it did: 11 instructions per sweep step; +1.2 % on cfg2)
+    uint32_t hs;
+    asm volatile("mov.u32 %0, %1;" : "=r"(hs) : "r"((uint32_t)__cvta_generic_to_shared(hist)));
+#define LS_LD(bin) lds_u32(hs + 128u * (uint32_t)(bin))
+#define LS_ST(bin, val) sts_u32(hs + 128u * (uint32_t)(bin), (val))
     const int n_cycles = a.p.n_cycles, cap_cycle = a.p.capture_cycle;
     const int BIG = 1 << 29;
 
@@ -400,7 +417,7 @@ __global__ void __launch_bounds__(128, SONICS_LS_MIN_BLOCKS) k_pcr_ls(const SimA
             const int wlo = __reduce_min_sync(SONICS_FULL, lo + sb);
             const int wend = __reduce_max_sync(SONICS_FULL, lo + bend);
             int carry = 0;
-            int prev = (valid && sb > 0) ? hist[(sb - 1) * 32] : 0; // finished value of bin b-1
+            int prev = (valid && sb > 0) ? LS_LD(sb - 1) : 0; // finished value of bin b-1
             float E_up = 0.0f, E_dn = 0.0f;
             if (valid) {
                 const float al = (float)(lo + sb);
@@ -416,7 +433,7 @@ __global__ void __launch_bounds__(128, SONICS_LS_MIN_BLOCKS) k_pcr_ls(const SimA
                 bool stutter = false;
                 float p_slip = 0.0f, p_upn = 0.0f;
                 if (in) {
-                    const int raw = hist[b * 32];
+                    const int raw = LS_LD(b);
                     cur = raw + carry;
                     carry = 0;
                     if (raw != 0) { // empty at cycle start: not amplified this cycle (:424)
@@ -455,7 +472,7 @@ __global__ void __launch_bounds__(128, SONICS_LS_MIN_BLOCKS) k_pcr_ls(const SimA
                     const int down = x1 - x2;    // mol_down
                     carry = down > 0 ? x2 : 0;   // sic: up-stutter only lands when mol_down > 0 (:473-476)
                     if (b > 0)
-                        hist[(b - 1) * 32] = prev + down;
+                        LS_ST(b - 1, prev + down);
                     if (down > 0 && b - 1 < live_lo)
                         live_lo = b - 1;
                     if (cur != 0 && b > live_hi)
@@ -466,7 +483,7 @@ __global__ void __launch_bounds__(128, SONICS_LS_MIN_BLOCKS) k_pcr_ls(const SimA
                 }
             }
             if (bend >= 0)
-                hist[bend * 32] = prev;
+                LS_ST(bend, prev);
         }
 
         // ---- lnL (+ readout) of the final pool, all lanes together ----

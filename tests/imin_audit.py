@@ -6,7 +6,7 @@ rejection trials only, no idle slots while neighbours retry -- read off the per-
 profiles/r02_k1_lockstep_ncu.txt / tools/ncu_sass.py (the instruction stream as compiled, not a lower bound of the
 algorithm):
 
-  BTRS draw (n min(p,q) >= 10)   77 set-up + trials x (33 Philox2x32-10 + 4 uniforms + 14 candidate / quick test +
+  BTRS draw (n min(p,q) >= 20)   77 set-up + trials x (33 Philox2x32-10 + 4 uniforms + 14 candidate / quick test +
                                  8 accept) + 0.21 x trials x 32 squeeze;   trials = (2.83 + 5.1 / b) / sqrt(2 pi),
                                  b = 1.15 + 2.53 sqrt(n p q)  (Hoermann 1993: hat area / pmf mass)
   inversion draw                 42 set-up + 38 Philox + uniform + 9 x (steps + 1);  steps = E[X] = n min(p,q)
@@ -46,7 +46,7 @@ def audit(name, n_sims=None, seed=1000):
         n = sc["n"][b].astype(np.float64)
         p = sc["p"][b].astype(np.float64)
         pp = np.minimum(p, 1.0 - p)
-        big = n * pp >= 10.0
+        big = n * pp >= 20.0   # SONICS_INV_BELOW (samplers.cuh)
         small = (~big) & (n > 0) & (p > 0) & (p < 1)
         spq = np.sqrt(n[big] * pp[big] * (1.0 - pp[big]))
         tot["btrs"] += big.sum()

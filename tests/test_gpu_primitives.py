@@ -49,7 +49,9 @@ def test_device_philox_stream_layout():
 
 BINOM_CASES = [(1, 0.3), (5, 0.5), (20, 0.3), (100, 0.05), (1000, 0.005), (300000, 2e-5), (40, 0.9), (12, 0.97),
                (100, 0.1), (200, 0.08), (1000, 0.0373), (5000, 0.5), (150000, 0.05), (14000, 0.4), (20000, 0.7),
-               (1200000, 0.0123), (3000000, 0.1), (7503, 0.9991), (37, 0.4999), (1000000, 0.5)]
+               (1200000, 0.0123), (3000000, 0.1), (7503, 0.9991), (37, 0.4999), (1000000, 0.5),
+               # either side of the inversion / BTRS switch at n min(p, q) = 20 (SONICS_INV_BELOW)
+               (150000, 1.3e-4), (2000000, 9.9e-6), (45, 0.44), (1999, 0.01), (2001, 0.01), (50, 0.6)]
 
 
 def _k1_request_mix():
