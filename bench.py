@@ -257,12 +257,17 @@ K1_SOURCES = ["sim_lockstep.cuh", "sim_kernel.cuh", "samplers.cuh", "rng.cuh", "
 
 
 def kernel_sha():
-    """Hash of the K1 sources: profiles/k1_counters.json is only valid for the code it was captured from."""
+    """Hash of the K1 sources (comments and white space stripped): profiles/k1_counters.json is only valid for the
+    code it was captured from."""
     import hashlib
+    import re
     h = hashlib.sha256()
     for f in K1_SOURCES:
-        with open(os.path.join(ROOT, "sonics_b200", "csrc", f), "rb") as fh:
-            h.update(fh.read())
+        with open(os.path.join(ROOT, "sonics_b200", "csrc", f), "r") as fh:
+            src = fh.read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        src = re.sub(r"//[^\n]*", "", src)
+        h.update(re.sub(r"\s+", "", src).encode())
     return h.hexdigest()[:16]
 
 

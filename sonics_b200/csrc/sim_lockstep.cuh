@@ -4,21 +4,22 @@
 // bit-identical lnL / group / identity / r^2 (tests/test_gpu_lockstep.py) -- scheduled differently:
 //
 //   k_sort_keys  one key per work unit from the simulation's priors (which depend on (seed, uid, j) only):
-//                genotype slot | start-allele group | quantised efficiency | down | up
+//                noise flag | start pair (absolute repeat counts) | reach of the noise | Morton(eff, down, up)
+//                -- see SortCfg below
 //   CUB radix sort of (key, unit)
 //   k_pcr_ls     warp w simulates 32 consecutive units of the sorted list in lockstep over
 //                (cycle, bin, draw stage).
 //
 // Why: in k_pcr lanes drift apart (different start alleles, efficiencies, rejection counts), half of the executed
 // instructions are the per-lane state machine, and the samplers run at 3-16 of 32 lanes (profiles/r01_k1a).  Lanes
-// that hold the same genotype, the same start alleles and neighbouring prior parameters walk the same bins with
+// that hold the same start alleles (of any genotype), the same noise reach and neighbouring prior parameters walk the same bins with
 // counts that differ by O(sqrt(n)), so in lockstep they take the same sampler (inversion / BTRS) at the same
 // (cycle, bin, stage) slot, the bin walk and the cycle boundary cost a few warp-uniform instructions per visit, and
 // all 32 lanes finish together, so the lnL (and the readout) runs fully converged inside the kernel: no pool
 // hand-off through HBM.  What remains divergent is what is random per draw: rejected trials and the Stirling test.
 //
-// A lane only touches bins [sb, bend] of its own sweep (exactly the bins k_pcr visits), so mixed warps (two
-// genotypes, different windows) stay correct; they are merely slower.
+// A lane only touches bins [sb, bend] of its own sweep (exactly the bins k_pcr visits) and the warp walks absolute
+// repeat counts, so warps that mix genotypes (different windows, reads, allele lists) are the normal case.
 #pragma once
 #include <stdint.h>
 

@@ -469,7 +469,9 @@ static int launch_simulate_lockstep(sonics_ctx *ctx, SimArgs &a, const TableInfo
     sc.al_bits = bits_for((int64_t)ti.max_al - ti.min_al + 1);
     sc.span_bits = bits_for((int64_t)ti.max_span + 1);
     sc.noise_bits = ti.any_noise ? 1 : 0;
-    sc.morton_bits = SONICS_LS_MORTON_BITS;
+    // one genotype per launch: a bit more per prior (+0.5 ... 1 %); with many genotypes finer fields scatter the
+    // lanes of a warp over the table and the result rows (-4 % on the cfg4 loop)
+    sc.morton_bits = SONICS_LS_MORTON_BITS + (n_slots == 1 ? 1 : 0);
     const int pair_bits = sc.noise_bits + sc.al_bits + sc.span_bits * (sc.noise_bits ? 3 : 1);
     // 32-bit keys (8 instead of 12 bytes per unit and pass) when one bit less per prior makes them fit
     if (pair_bits + 3 * sc.morton_bits > 32 && pair_bits + 3 * (sc.morton_bits - 1) <= 32)
