@@ -161,6 +161,17 @@ WORKER = textwrap.dedent("""
                           compute(whole.allele_off, whole.allele, whole.reads, whole.noise_coef, whole.uids(0)), whole)
         assert open(out_path).read() == open(out_path + ".single").read()
         assert not os.path.exists(out_path + ".part0") and not os.path.exists(out_path + ".part1")
+        # a longer file of an earlier run under the same name: the join must cut it to the new length
+        open(out_path + ".auto", "w").write("x" * (os.path.getsize(out_path) + 5000))
+    dist.barrier()
+    # the automatic piece plan (a short first piece per rank, then equal pieces, the same number for every rank)
+    driver.PIECE_BYTES = 900
+    driver._run_vcf_ranks(vcf_path, constants, None, options, 5, 65536, out_path + ".auto", rank, world,
+                          compute=compute)
+    dist.barrier()
+    if rank == 0:
+        assert driver.LAST_TIMINGS["pieces_total"] %% world == 0 and driver.LAST_TIMINGS["pieces_total"] >= 2 * world
+        assert open(out_path + ".auto").read() == open(out_path + ".single").read()
         print("RANKS_OK", whole.n_sim)
     dist.destroy_process_group()
 """)
@@ -226,6 +237,30 @@ def test_two_rank_gloo_vcf_ingest_simulate_write(tmp_path):
                           str(tmp_path / "out.txt")], capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "RANKS_OK" in out.stdout
+
+
+def test_piece_plan_tiles_the_file_evenly(tmp_path):
+    """even_piece_bytes / pieces_of(heads): the pieces tile the file without gap or overlap, every rank gets the same
+    number of them, and (files large enough for it) each rank starts on a short piece."""
+    from sonics_b200 import hostio
+    path = str(tmp_path / "f.bin")
+    for size in (1, 99, 3000, 70_001, 3_000_000, 50_000_000):
+        with open(path, "wb") as f:
+            f.truncate(size)
+        for world in (1, 2, 3, 4, 8):
+            head = driver.even_piece_bytes(size, world) // 4
+            body = driver.even_piece_bytes(max(0, size - world * head), world)
+            pcs = hostio.pieces_of(path, body, world, head)
+            assert pcs[0][0] == 0 and pcs[-1][1] == -1
+            assert all(pcs[i][1] == pcs[i + 1][0] for i in range(len(pcs) - 1))
+            assert all(b > a for a, b in pcs[:-1]) and pcs[-1][0] < size
+            counts = [len(range(r, len(pcs), world)) for r in range(world)]
+            if size >= 64 * world:
+                assert max(counts) - min(counts) <= 1, (size, world, counts)
+            if size >= 3_000_000:
+                assert len(set(counts)) == 1 and counts[0] >= 2, (size, world, counts)
+                assert all(pcs[r][1] - pcs[r][0] == head for r in range(world))
+                assert max(b - a for a, b in pcs[:-1]) <= driver.PIECE_BYTES
 
 
 def test_shard_jobs_cover_the_batch_with_their_own_keys():
