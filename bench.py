@@ -551,10 +551,23 @@ def main():
             "cfg1": dict(timed_rate("8|5;9|113;10|89", {}, n // 2), what="README example, defaults"),
             "cfg3": dict(timed_rate(cfg3, dict(n_cycles=30, capture_cycle=16), n // 16),
                          what="40 input alleles, 30 cycles, capture at 16, automatic noise"),
+            "cfg2_fast_samplers": None,
             "cfg2_with_readout": dict(timed_rate(CFG2, {}, n // 2, readout=True),
                                       what="cfg2 with the per-simulation sequencing readout, identity and r^2 "
                                            "(sonics.pyx:341-384) -- everything the reference's one_repeat() does"),
         }
+
+    if rank == 0:
+        # beside the exact number, never instead of it: the opt-in approximate sampler (sonics_set_samplers)
+        e.set_samplers("fast", 100.0)
+        try:
+            configs["cfg2_fast_samplers"] = dict(
+                timed_rate(CFG2, {}, n // 2),
+                what="cfg2 with SONICS_SAMPLERS_FAST, min_npq = 100: binomial draws with n p q >= 100 from a normal / "
+                     "Cornish-Fisher approximation (opt-in, not the reference's sampler; gates in "
+                     "tests/test_gpu_fast_samplers.py); `value` above is the exact mode")
+        finally:
+            e.set_samplers("exact")
 
     # ---- genotyping: strong scaling of a cfg5-style VCF, file to file, across all ranks ----
     geno_scale = None

@@ -174,6 +174,17 @@ int sonics_set_kernel(sonics_ctx *ctx, int kernel);
  * sort only decides which lane runs which simulation: results never depend on it (tuning knob; env
  * SONICS_SORT_BITS=e,d,u sets the initial value). */
 int sonics_set_sort_bits(sonics_ctx *ctx, int eff_bits, int down_bits, int up_bits);
+/* Samplers of the PCR cycles (lockstep form).
+ *   SONICS_SAMPLERS_EXACT (default)  inversion / BTRS: exact binomial variates (chi^2 against the pmf at 2e7 draws);
+ *   SONICS_SAMPLERS_FAST             opt-in: binomial draws with n p q >= min_npq (>= 20; 100 is the tested setting)
+ *                                    come from one normal deviate through the first Cornish-Fisher term, rounded
+ *                                    (|cdf error| <= 1.2e-2 / (n p q)); smaller draws stay exact.  No rejection
+ *                                    rounds, ~1.5x the reactions/s; passes the same KS and concordance gates
+ *                                    (tests/test_gpu_fast_samplers.py) but is not the reference's sampler: results
+ *                                    of the two modes differ draw by draw.  A run (and its replay, K4) must use one
+ *                                    mode throughout.  The persistent / traced form is always exact. */
+enum { SONICS_SAMPLERS_EXACT = 0, SONICS_SAMPLERS_FAST = 1 };
+int sonics_set_samplers(sonics_ctx *ctx, int mode, double min_npq);
 /* Lockstep form: which simulations share a warp.
  *   SONICS_SORT_PAIR_MAJOR (default)  noise flag | the two start alleles as absolute repeat counts | reach of the noise
  *                                     molecules below / above them | the three priors, Morton-interleaved.  A reaction
@@ -249,7 +260,8 @@ int sonics_genotype_batch(sonics_ctx *ctx, const SonicsParams *params, int n_gt,
  * sonics_debug_pairs:   n_pairs x 2 u32 of the Philox2x32-10 stream the PCR cycles draw from
  *                       (key = sim_lo ^ seed_lo, counter = (pair index | sim_hi << 24, uid ^ seed_hi)).
  * sonics_debug_sample:  count draws, one per thread (thread t uses sim = t), of
- *      kind 0: Binomial(n, p)    kind 1: Poisson(lam = p)
+ *      kind 0: Binomial(n, p)    kind 1: Poisson(lam = p)    kind 2: Binomial(n, p) from the approximate sampler
+ *      of SONICS_SAMPLERS_FAST (whatever n p q is)
  * into dev_out (int32).  Both synchronous; dev_out is caller-owned device memory. */
 /* sonics_debug_counters: while dev_counters (16 x u64 of caller-owned device memory, zeroed by the
  * caller) is non-NULL, sonics_simulate accumulates K1 control-flow statistics into it: [0] passes,

@@ -89,6 +89,7 @@ PROTOTYPES = {
     "sonics_set_kernel": (_I, [_P, _I]),
     "sonics_set_sort_bits": (_I, [_P, _I, _I, _I]),
     "sonics_set_sort_mode": (_I, [_P, _I]),
+    "sonics_set_samplers": (_I, [_P, _I, ctypes.c_double]),
     "sonics_debug_readout": (_I, [_P, _P]),
     "sonics_evaluate": (_I, [_P, ctypes.POINTER(SonicsParams), _P, _I, _P, _I, _I64, _I64, _P, _P, _P, _P, _I, _P, _P,
                              _SZ, _P]),

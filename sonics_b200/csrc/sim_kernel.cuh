@@ -119,6 +119,7 @@ struct SimArgs {
     int32_t *readout_dump;
     // lockstep kernel (sim_lockstep.cuh): the launch's work units in execution order (nullable = identity)
     const uint32_t *order;
+    float fast_npq; // approximate sampler for binomial draws with n p q >= this (k_pcr_ls<.., true> only)
 };
 
 // descriptors of the readout -> the per-simulation arrays, or (replay mode, K4) the genotype's verdict
@@ -259,6 +260,11 @@ __global__ void k_debug_sample(int kind, int n, double p, int64_t count, uint64_
     if (kind == 0) {
         const uint4 b = r.block4();
         out[t] = binomial(r, n, (float)p, b.x, b.y, rcp_tab);
+    } else if (kind == 2) { // the approximate sampler, as binomial_ls<true> calls it
+        const uint4 b = r.block4();
+        const float pf = (float)p;
+        const int k = binomial_normal(n, pf > 0.5f ? 1.0f - pf : pf, b.x, b.y);
+        out[t] = pf > 0.5f ? n - k : k;
     } else {
         out[t] = poisson(r, (float)p);
     }

@@ -138,7 +138,10 @@ __global__ void k_sort_keys(const SimArgs a, const SortCfg c, KeyT *keys, uint32
 // ---- lockstep samplers: every lane of the warp calls these together ---------------------------------------
 // Same pieces, same random words per draw as the state machine of k_pcr: an inversion takes one pair of its
 // simulation's stream, a rejection sampler one pair per trial, the Stirling test none.
-__device__ __forceinline__ int binomial_ls(PairRng &rng, int n, float p, const float *rcp_tab)
+// FAST (sonics_set_samplers): draws with n p q >= fast_npq take binomial_normal() instead of BTRS -- one block, no
+// rejection.  The exact instantiation (FAST = false) contains none of it.
+template <bool FAST>
+__device__ __forceinline__ int binomial_ls(PairRng &rng, int n, float p, const float *rcp_tab, float fast_npq)
 {
     int x = 0;
     bool need = n > 0 && p > 0.0f; // !(p > 0): degenerate priors only
@@ -149,7 +152,15 @@ __device__ __forceinline__ int binomial_ls(PairRng &rng, int n, float p, const f
     const bool flip = p > 0.5f;
     const float pp = flip ? 1.0f - p : p;
     const bool inv = need && (float)n * pp < SONICS_INV_BELOW;
-    bool pend = need && !inv;
+    const bool fast = FAST && need && !inv && (float)n * pp * (1.0f - pp) >= fast_npq;
+    bool pend = need && !inv && !fast;
+    if (FAST && __any_sync(SONICS_FULL, fast)) {
+        if (fast) {
+            const uint2 w = rng.pair();
+            const int k = binomial_normal(n, pp, w.x, w.y);
+            x = flip ? n - k : k;
+        }
+    }
     int guard = 0;
     DrawState ds;
 #ifdef SONICS_LS_STATS
@@ -267,7 +278,7 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, int v)
     asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-template <bool READOUT>
+template <bool READOUT, bool FAST>
 __global__ void __launch_bounds__(128, SONICS_LS_MIN_BLOCKS) k_pcr_ls(const SimArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -460,7 +471,7 @@ __global__ void __launch_bounds__(128, SONICS_LS_MIN_BLOCKS) k_pcr_ls(const SimA
                         break; // nothing amplified / slipped in any lane: the later stages draw from 0
                     LS_STAT(48 + stage, 1);
                     LS_STAT(52 + stage, __popc(__ballot_sync(SONICS_FULL, dn > 0)));
-                    const int x = binomial_ls(rng, dn, dp, rcp_tab);
+                    const int x = binomial_ls<FAST>(rng, dn, dp, rcp_tab, a.fast_npq);
                     if (stage == 0)
                         x0 = x;
                     else if (stage == 1)

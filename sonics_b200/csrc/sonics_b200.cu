@@ -62,6 +62,7 @@ struct sonics_ctx {
     int kernel;              // SONICS_KERNEL_*: which form of K1 sonics_simulate launches
     int sort_bits[3];        // lockstep sort key: bits of efficiency / down / up (-1 = automatic)
     int sort_mode;           // SONICS_SORT_*
+    float fast_npq;          // > 0: approximate sampler for binomial draws with n p q >= this (sonics_set_samplers)
     std::map<const void *, TableInfo> tables;
 };
 
@@ -119,6 +120,7 @@ int sonics_create(int device, sonics_ctx **out)
     if (const char *e = getenv("SONICS_SORT_BITS"))
         sscanf(e, "%d,%d,%d", &c->sort_bits[0], &c->sort_bits[1], &c->sort_bits[2]);
     c->sort_mode = SONICS_SORT_PAIR_MAJOR;
+    c->fast_npq = 0.0f;
     if (const char *e = getenv("SONICS_SORT_MODE"))
         if (!strcmp(e, "slot"))
             c->sort_mode = SONICS_SORT_SLOT_MAJOR;
@@ -495,7 +497,9 @@ static int launch_simulate_lockstep(sonics_ctx *ctx, SimArgs &a, const TableInfo
     if (key_bits > 64)
         return fail(SONICS_ERR_RANGE, "sort key of %d bits", key_bits);
 
-    auto pcr = readout ? k_pcr_ls<true> : k_pcr_ls<false>;
+    a.fast_npq = ctx->fast_npq;
+    auto pcr = ctx->fast_npq > 0.0f ? (readout ? k_pcr_ls<true, true> : k_pcr_ls<false, true>)
+                                    : (readout ? k_pcr_ls<true, false> : k_pcr_ls<false, false>);
     const size_t per_warp = warp_smem_bytes(a.Wcap);
     int wpb = (int)std::min<size_t>(4, (200 * 1024) / per_warp);
     if (wpb < 1)
@@ -591,6 +595,16 @@ int sonics_set_kernel(sonics_ctx *ctx, int kernel)
     if (!ctx || kernel < SONICS_KERNEL_AUTO || kernel > SONICS_KERNEL_LOCKSTEP)
         return fail(SONICS_ERR_ARG, "sonics_set_kernel: bad argument");
     ctx->kernel = kernel;
+    return SONICS_OK;
+}
+
+int sonics_set_samplers(sonics_ctx *ctx, int mode, double min_npq)
+{
+    if (!ctx || (mode != SONICS_SAMPLERS_EXACT && mode != SONICS_SAMPLERS_FAST))
+        return fail(SONICS_ERR_ARG, "sonics_set_samplers: bad argument");
+    if (mode == SONICS_SAMPLERS_FAST && !(min_npq >= 20.0))
+        return fail(SONICS_ERR_RANGE, "sonics_set_samplers: the approximate sampler needs n p q >= 20 (got %g)", min_npq);
+    ctx->fast_npq = mode == SONICS_SAMPLERS_FAST ? (float)min_npq : 0.0f;
     return SONICS_OK;
 }
 
@@ -713,7 +727,7 @@ int sonics_debug_pairs(sonics_ctx *ctx, uint64_t seed, uint64_t sim, uint32_t ui
 
 int sonics_debug_sample(sonics_ctx *ctx, int kind, int n, double p, int64_t count, uint64_t seed, int32_t *dev_out)
 {
-    if (!ctx || !dev_out || count <= 0 || (kind != 0 && kind != 1))
+    if (!ctx || !dev_out || count <= 0 || kind < 0 || kind > 2)
         return fail(SONICS_ERR_ARG, "sonics_debug_sample: bad argument");
     CUDA_OK(cudaSetDevice(ctx->device));
     k_debug_sample<<<(unsigned)((count + 255) / 256), 256>>>(kind, n, p, count, seed, dev_out);

@@ -77,6 +77,11 @@ def build_parser():
                    help="Philox seed for a reproducible run (default: fresh entropy, like the reference).")
     p.add_argument("--gpus", type=int, default=1, help="GPUs of this box to shard the genotype list over.")
     p.add_argument("--chunk", type=int, default=131072, help="Genotypes per device batch.")
+    p.add_argument("--fast_samplers", type=float, nargs="?", const=100.0, default=0.0, metavar="MIN_NPQ",
+                   help="Opt-in approximate sampler (not in the reference): binomial draws with n*p*q >= MIN_NPQ "
+                        "(default 100, at least 20) come from a normal / Cornish-Fisher approximation instead of the "
+                        "exact rejection sampler. About 1.5x faster; passes the same KS / concordance gates, but "
+                        "results differ draw by draw from the default mode.")
     return p
 
 
@@ -224,6 +229,9 @@ def run_batch_verdicts(allele_off, allele, reads, noise, constants, ranges, opti
     (default: the position in this batch)."""
     from . import engine as eng
     e = sonics_mod.engine(device)
+    # --fast_samplers (main() exports it so that spawned per-GPU workers see it too); the dicts keep the reference's keys
+    fast = float(os.environ.get("SONICS_FAST_SAMPLERS", "0") or 0.0)
+    e.set_samplers("fast" if fast > 0 else "exact", fast if fast > 0 else 100.0)
     params = eng.params_from_dicts(constants, ranges, options)
     n = len(noise)
     uids = np.arange(n, dtype=np.uint32) if uids is None else np.ascontiguousarray(uids, dtype=np.uint32)
@@ -525,6 +533,10 @@ def main(argv=None):
     logging.debug("SONiCS run with the following options:")
     logging.debug(args)
     constants, ranges, options = dicts_from_args(args)
+    if args.fast_samplers:
+        os.environ["SONICS_FAST_SAMPLERS"] = repr(float(args.fast_samplers))
+    else:
+        os.environ.pop("SONICS_FAST_SAMPLERS", None)
     run_sonics(args.INPUT, constants, ranges, options, seed=args.seed, gpus=args.gpus, chunk=args.chunk)
 
 

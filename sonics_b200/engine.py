@@ -130,6 +130,11 @@ class Engine:
         check(self.lib.sonics_set_kernel(self.ctx, k))
         self.kernel = k
 
+    def set_samplers(self, mode="exact", min_npq=100.0):
+        """'exact' (default): inversion / BTRS.  'fast': binomial draws with n p q >= min_npq from the normal /
+        Cornish-Fisher approximation (sonics_set_samplers; opt-in, not the reference's sampler)."""
+        check(self.lib.sonics_set_samplers(self.ctx, {"exact": 0, "fast": 1}[mode], float(min_npq)))
+
     def close(self):
         if getattr(self, "ctx", None):
             self.lib.sonics_destroy(self.ctx)
@@ -190,7 +195,7 @@ class Engine:
 
     def debug_sample(self, kind, n, p, count, seed):
         out = self.torch.empty(count, dtype=self.torch.int32, device=self.device)
-        check(self.lib.sonics_debug_sample(self.ctx, {"binomial": 0, "poisson": 1}[kind], int(n), float(p), int(count),
+        check(self.lib.sonics_debug_sample(self.ctx, {"binomial": 0, "poisson": 1, "binomial_fast": 2}[kind], int(n), float(p), int(count),
                                            int(seed), out.data_ptr()))
         return out.cpu().numpy()
 

@@ -4,6 +4,7 @@ btrs_trial() accepts / rejects a candidate k without evaluating ln f(k)/f(m) whe
 [t - rho, t + rho], a quartic in k - m with a fifth-order remainder bound.  That is only exact if the interval
 really brackets ln f(k)/f(m) for every k in the stated range.  Checked here against the exact log-pmf ratio."""
 import numpy as np
+import pytest
 from scipy.special import gammaln
 
 
@@ -206,3 +207,36 @@ def test_exact_test_in_deviance_form_is_accurate_in_fp32():
     assert checked > 100000
     assert worst_core < 2e-5, worst_core   # the Stirling series is the limit where k (or n - k) < 10:
     assert worst < 4e-4, worst             # fc(0) is off by 3e-4, fc(1) by 2e-5 (test_stirling_tail_series)
+
+
+def _cf_cdf(n, p, ks):
+    """cdf of the approximate sampler (samplers.cuh: binomial_normal) in exact arithmetic: the normal deviate z with
+    n p + sqrt(n p q - 1/12) z + (q - p)(z^2 - 1)/6 < k + 1/2."""
+    import scipy.stats as st
+    q = 1.0 - p
+    s, g, mu = np.sqrt(n * p * q - 1.0 / 12.0), (q - p) / 6.0, n * p
+    b = ks + 0.5
+    if abs(g) < 1e-12:
+        z = (b - mu) / s
+    else:
+        disc = s * s - 4.0 * g * (mu - g - b)
+        z = np.where(disc > 0, (-s + np.sqrt(np.maximum(disc, 0.0))) / (2.0 * g), -np.inf)
+    return st.norm.cdf(z)
+
+
+@pytest.mark.parametrize("npq", [20, 100, 1000, 1e5])
+def test_fast_sampler_formula_error_bound(npq):
+    """The opt-in approximate sampler (SONICS_SAMPLERS_FAST): |cdf - binomial cdf| <= 1.2e-2 / (n p q), pmf within
+    0.9 % / 0.08 % inside three sigma at n p q = 100 / 1000 -- the numbers quoted in samplers.cuh and the header."""
+    import scipy.stats as st
+    for p in (0.5, 0.3, 0.1, 0.01, 1e-4):
+        n = int(round(npq / (p * (1 - p))))
+        s, mu = np.sqrt(n * p * (1 - p)), n * p
+        ks = np.arange(max(0, int(mu - 8 * s)), min(n, int(mu + 8 * s)) + 1).astype(np.float64)
+        ap = _cf_cdf(n, p, ks)
+        assert np.abs(ap - st.binom.cdf(ks, n, p)).max() <= 1.2e-2 / npq, (npq, p)
+        pa = np.diff(np.concatenate([_cf_cdf(n, p, np.array([ks[0] - 1.0])), ap]))
+        pe = st.binom.pmf(ks, n, p)
+        c = np.abs(ks - mu) <= 3 * s
+        rel = np.abs(pa[c] / pe[c] - 1).max()
+        assert rel <= {20: 0.10, 100: 0.009, 1000: 0.0008, 1e5: 1e-5}[npq], (npq, p, rel)

@@ -16,6 +16,8 @@ n_samples = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 noisy = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0
 cov = (2000, 10000) if noisy > 0 else (50, 1000)
 e = eng.Engine(0)
+if float(os.environ.get("SONICS_FAST_SAMPLERS", "0") or 0) > 0:   # the opt-in approximate sampler
+    e.set_samplers("fast", float(os.environ["SONICS_FAST_SAMPLERS"]))
 loci = synth_vcf.make_genotypes(n_loci, n_samples, seed=20261019, cov=cov, noisy=noisy)
 constants = {"one_allele_threshold": 45, "noise_threshold": 0.05}
 work = [p for k, p in (driver.prefilter(t, constants, {"monte_carlo": False}) for t in synth_vcf.genotype_strings(loci))
