@@ -4,6 +4,8 @@ Binomial draws with n p q >= min_npq come from one normal deviate through the fi
 BTRS.  It is NOT the reference's sampler and not the default; what it has to pass are the north star's own gates --
 lnL distributions indistinguishable from the oracle's by KS (p > 0.01 at >= 1e5 simulations per group) and
 genotype calls identical on >= 99.5 % of the rows that PASS on both sides -- plus a direct bound on the sampled cdf."""
+import os
+
 import numpy as np
 import pytest
 import scipy.stats as st
@@ -108,3 +110,24 @@ def test_concordance_fast(fast_engine):
     assert g_o[1] >= 0.995 and g_o[2] >= 0.5 * n
     se = np.sqrt(2 * max(o_o[0] * (1 - o_o[0]), 1e-4) / n)
     assert g_o[0] >= o_o[0] - 4 * se - 0.005, (g_o, o_o)
+
+
+def test_cli_flag(tmp_path):
+    """`sonics --fast_samplers [MIN_NPQ]`: same row layout, the README example still calls 9/10 PASS; the flag changes
+    the draws (another lnL than the default mode under the same seed) and is rejected below n p q = 20."""
+    import subprocess
+    import sys
+    root = os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+
+    def run(*extra):
+        return subprocess.run([sys.executable, os.path.join(root, "bin", "sonics"), CFG1, "-o", str(tmp_path),
+                               "--seed", "5"] + list(extra), capture_output=True, text=True, timeout=600)
+    rows = {}
+    for name, extra in (("exact", []), ("fast", ["--fast_samplers"]), ("fast50", ["--fast_samplers", "50"])):
+        out = run("-n", name + ".txt", *extra)
+        assert out.returncode == 0, out.stderr[-2000:]
+        rows[name] = open(os.path.join(str(tmp_path), name + ".txt")).read().split("\n")[1].split("\t")
+        assert rows[name][3] == "9/10" and rows[name][7] == "PASS" and len(rows[name]) == 13
+    assert rows["fast"][6] != rows["exact"][6] and rows["fast50"][6] != rows["fast"][6]
+    bad = run("-n", "bad.txt", "--fast_samplers", "5")
+    assert bad.returncode != 0 and "n p q >= 20" in bad.stderr
