@@ -21,8 +21,9 @@ same locus (weak scaling, no collective on the data path); rank 0 prints ONE JSO
                   (thread-instructions a simulation needs / thread-instruction peak) say how much of the
                   issued work is useful; traffic = DRAM bytes of every kernel of the step
   hbm_roofline    the HBM view (10 B/reaction of mandatory traffic): tiny by construction
-  configs         device-resident rates of cfg1 / cfg3, and cfg2 with the per-simulation readout
-                  (identity / r^2) switched on -- the work the reference's one_repeat() does
+  configs         device-resident rates of cfg1 / cfg3, cfg2 with the per-simulation readout (identity / r^2)
+                  switched on -- the work the reference's one_repeat() does -- and cfg2 with the opt-in approximate
+                  sampler (SONICS_SAMPLERS_FAST, min_npq 100): beside `value`, which is always the exact mode
   genotyping      the other half of BASELINE.json's metric, loci genotyped/s: cfg4 through the C-ABI with
                   host buffers, a cfg5-style noisy VCF file to file across all ranks (strong scaling: seconds,
                   genotypes/s, sha256 of the output) and, at N = 1, the reference's monte_carlo() on the host
