@@ -227,8 +227,18 @@ def genotyping_throughput(e, eng, drop_in, n_loci=10000, n_samples=8):
     t0 = time.perf_counter()
     v = e.genotype_batch(params, off, al, rd, noise, 1000, seed=20261019)
     dt = time.perf_counter() - t0
+    n_launch = int(e.launches - l0)
     reps = v["run_reps"].astype(np.int64)
     filt, cnt = np.unique(v["filter"], return_counts=True)
+    # the same loop with the opt-in approximate sampler (beside the exact figure, never instead of it)
+    e.set_samplers("fast", 100.0)
+    try:
+        t0 = time.perf_counter()
+        vf = e.genotype_batch(params, off, al, rd, noise, 1000, seed=20261019)
+        dt_fast = time.perf_counter() - t0
+    finally:
+        e.set_samplers("exact")
+    same_call = float(np.mean((vf["allele_lo"] == v["allele_lo"]) & (vf["allele_hi"] == v["allele_hi"])))
     # the same job file to file: VCF text -> native ingest + pre-filters -> GPU loop -> sonics_out.txt
     import tempfile
     with tempfile.TemporaryDirectory() as d:
@@ -247,7 +257,10 @@ def genotyping_throughput(e, eng, drop_in, n_loci=10000, n_samples=8):
             "reactions": int(reps.sum()), "reactions_per_s": float(reps.sum() / dt),
             "repeats_hist": {str(k): int((reps == k).sum()) for k in (100, 500, 1000)},
             "filter_hist": {drop_in.filter_string(int(f)) or "(none)": int(c) for f, c in zip(filt, cnt)},
-            "gpu_launches": int(e.launches - l0),
+            "gpu_launches": n_launch,
+            "fast_samplers": {"value": len(work) / dt_fast, "unit": "genotypes/s", "seconds": dt_fast, "min_npq": 100,
+                              "same_genotype_as_exact": same_call,
+                              "what": "the same call with SONICS_SAMPLERS_FAST (opt-in; `value` is the exact mode)"},
             "file_to_file": {"value": n_lines / file_dt, "unit": "genotypes/s", "seconds": file_dt, "rows": n_lines,
                              "what": "sonics -m cfg4.vcf: native VCF ingest + pre-filters, GPU loop, native row writer"},
             "workload": "cfg4: synthetic VCF %d loci x %d samples, coverage 50-1000, -r 1000, default filters; "
