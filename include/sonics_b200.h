@@ -219,11 +219,11 @@ int sonics_evaluate(sonics_ctx *ctx, const SonicsParams *params, const void *dev
                     const uint16_t *dev_group, const double *dev_identity, const float *dev_rsq, int final_round,
                     SonicsVerdict *dev_verdict, void *dev_scratch, size_t dev_scratch_bytes, void *stream);
 /* Scratch sonics_evaluate needs when n_run > SONICS_STATS_MAX_REPS or a genotype has more than 2048 start-allele
- * groups (statistics over global memory: CUB sort, then the on-chip algorithm on global arrays; --monte_carlo: one
- * genotype at a time); 0 otherwise, where dev_scratch may be NULL.  Size for one genotype = the minimum. */
+ * groups (statistics over global memory: one segmented CUB sort, then the on-chip algorithm on global arrays, both
+ * modes); 0 otherwise, where dev_scratch may be NULL.  Size for one genotype = the minimum. */
 size_t sonics_stats_scratch_bytes(int64_t n_run, int max_alleles, int random_start);
-/* The same for n_active genotypes in one statistics launch (default mode: global-memory form of the on-chip
- * kernel, 26 bytes per simulation; a smaller buffer, down to the one-genotype size, means several launches). */
+/* The same for n_active genotypes in one statistics launch (26 bytes per simulation; a smaller buffer, down to the
+ * one-genotype size, means several launches). */
 size_t sonics_stats_scratch_bytes_batch(int n_active, int64_t n_run, int max_alleles, int random_start);
 
 /* K4: replay simulation dev_verdict[g].best_sim of every listed genotype (same Philox stream, hence
